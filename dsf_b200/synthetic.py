@@ -122,6 +122,16 @@ def make_synthetic_mano(seed: int = 0) -> dict:
     }
 
 
+_J0_CACHE = {}
+
+
+def _rest_wrist_joint(seed: int = 0) -> np.ndarray:
+    if seed not in _J0_CACHE:
+        m = make_synthetic_mano(seed)
+        _J0_CACHE[seed] = np.asarray(m["J_regressor"].toarray()[0] @ m["v_template"])
+    return _J0_CACHE[seed]
+
+
 def write_mano_pkl(directory: str, seed: int = 0) -> str:
     """Write ``<directory>/MANO_RIGHT.pkl`` (the file name Render.__init__ appends,
     mano_layer.py:931) and return its path."""
@@ -144,7 +154,15 @@ def sample_fit_inputs(batch: int, seed: int = 0, cube_mm: float = 250.0) -> dict
     theta = np.clip(rng.randn(batch, 45), -2, 2)
     beta = rng.randn(batch, 10)
     scale = rng.uniform(0.9, 1.1, (batch, 1))
-    trans = rng.uniform(-0.1, 0.1, (batch, 3))
+    # MANO rotates about the wrist joint; translate so the rotated hand stays centred in the
+    # cube (as a real crop around the hand's centre of mass would be), plus the +-0.1 jitter
+    j0 = _rest_wrist_joint()
+    ang = np.linalg.norm(quat, axis=1, keepdims=True)
+    ax = quat / np.maximum(ang, 1e-12)
+    v = -j0[None]
+    rot = (v * np.cos(ang) + np.cross(ax, v) * np.sin(ang)
+           + ax * (ax * v).sum(1, keepdims=True) * (1 - np.cos(ang)))
+    trans = -(rot + j0[None]) * scale * 8.0 + rng.uniform(-0.1, 0.1, (batch, 3))
     params = np.concatenate([quat, theta, beta, scale, trans], 1)
     tgt = params.copy()
     tgt[:, :48] += rng.randn(batch, 48) * 0.1
