@@ -1,0 +1,792 @@
+// dsf_b200 - MANO hand layer for sm_100a: pose/chain kernel, blend-shape GEMM, skinning kernel and
+// their backward.  Replaces render_model/mano_layer.py:573-770 (see include/dsf_b200.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error / launch bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+void dsf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void dsf_count_launch(int n) { g_launches += n; }
+void dsf_reset_launch_count() { g_launches = 0; }
+
+extern "C" const char* dsf_last_error_string(void) { return g_err; }
+extern "C" int dsf_version(void) { return 100; }
+extern "C" int dsf_last_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------------
+// M0: constants
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T** dst, const T* src, size_t n) {
+    DSF_CHECK_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+    DSF_CHECK_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return DSF_OK;
+}
+
+void dsf_build_collision_mask(float* m);   // coll.cu
+
+extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
+    DSF_REQUIRE(host && out, "null host/out");
+    DSF_REQUIRE(host->v_template && host->shapedirs && host->posedirs && host->j_regressor &&
+                    host->hands_comp && host->hands_mean && host->weights && host->parents && host->faces,
+                "null constant array");
+    DSF_REQUIRE(host->n_faces > 0 && host->n_faces < 65536, "n_faces out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        dsf_set_error("no CUDA device: dsf_b200 has no CPU fallback");
+        return DSF_ERR_NO_DEVICE;
+    }
+    DsfMano* h = (DsfMano*)calloc(1, sizeof(DsfMano));
+    DSF_CHECK_CUDA(cudaGetDevice(&h->device));
+
+    // kinematic tree levels (parents[i] < i, mano_layer.py:753-757 walks i in order)
+    h->parents[0] = -1;
+    h->level[0] = 0;
+    h->maxlevel = 0;
+    for (int i = 1; i < NJ; ++i) {
+        int p = host->parents[i];
+        if (p < 0 || p >= i) {
+            dsf_set_error("parents[%d]=%d must be in [0,%d)", i, p, i);
+            free(h);
+            return DSF_ERR_BAD_ARG;
+        }
+        h->parents[i] = p;
+        h->level[i] = h->level[p] + 1;
+        if (h->level[i] > h->maxlevel) h->maxlevel = h->level[i];
+    }
+    for (int i = 0; i < host->n_faces * 3; ++i) {
+        if (host->faces[i] < 0 || host->faces[i] >= NVW) {
+            dsf_set_error("face index %d out of range", host->faces[i]);
+            free(h);
+            return DSF_ERR_BAD_ARG;
+        }
+    }
+
+    std::vector<float> D((size_t)KP * NP, 0.f), DT((size_t)NP * KP, 0.f), vt(NP, 0.f);
+    for (int k = 0; k < 10; ++k)
+        for (int n = 0; n < NV * 3; ++n) D[(size_t)k * NP + n] = host->shapedirs[(size_t)k * NV * 3 + n];
+    for (int k = 0; k < 135; ++k)
+        for (int n = 0; n < NV * 3; ++n) D[(size_t)(10 + k) * NP + n] = host->posedirs[(size_t)k * NV * 3 + n];
+    for (int k = 0; k < KP; ++k)
+        for (int n = 0; n < NP; ++n) DT[(size_t)n * KP + k] = D[(size_t)k * NP + n];
+    for (int n = 0; n < NV * 3; ++n) vt[n] = host->v_template[n];
+
+    // rest joints as an affine function of beta: J = Jt + sum_b beta_b JS[b]   (mano_layer.py:586-591)
+    std::vector<float> Jt(NJ * 3), JS(10 * NJ * 3);
+    for (int j = 0; j < NJ; ++j)
+        for (int c = 0; c < 3; ++c) {
+            double a = 0;
+            for (int v = 0; v < NV; ++v) a += (double)host->j_regressor[v * NJ + j] * host->v_template[v * 3 + c];
+            Jt[j * 3 + c] = (float)a;
+            for (int b = 0; b < 10; ++b) {
+                double s = 0;
+                for (int v = 0; v < NV; ++v)
+                    s += (double)host->j_regressor[v * NJ + j] * host->shapedirs[(size_t)b * NV * 3 + v * 3 + c];
+                JS[(b * NJ + j) * 3 + c] = (float)s;
+            }
+        }
+    // CSR of the regressor (joint-major), keeps every non-zero
+    std::vector<int> ptr(NJ + 1, 0), idx;
+    std::vector<float> w;
+    for (int j = 0; j < NJ; ++j) {
+        for (int v = 0; v < NV; ++v) {
+            float x = host->j_regressor[v * NJ + j];
+            if (x != 0.f) {
+                idx.push_back(v);
+                w.push_back(x);
+            }
+        }
+        ptr[j + 1] = (int)idx.size();
+    }
+    h->jr_nnz = (int)idx.size();
+    if (idx.empty()) { idx.push_back(0); w.push_back(0.f); }
+    std::vector<float> mask(DSF_NSPHERE * DSF_NSPHERE);
+    dsf_build_collision_mask(mask.data());
+
+    int rc = 0;
+    rc |= upload(&h->Dmat, D.data(), D.size());
+    rc |= upload(&h->DmatT, DT.data(), DT.size());
+    rc |= upload(&h->vt, vt.data(), vt.size());
+    rc |= upload(&h->W, host->weights, (size_t)NV * NJ);
+    rc |= upload(&h->comp, host->hands_comp, 45 * 45);
+    rc |= upload(&h->mean, host->hands_mean, 45);
+    rc |= upload(&h->Jt, Jt.data(), Jt.size());
+    rc |= upload(&h->JS, JS.data(), JS.size());
+    rc |= upload(&h->jr_ptr, ptr.data(), ptr.size());
+    rc |= upload(&h->jr_idx, idx.data(), idx.size());
+    rc |= upload(&h->jr_w, w.data(), w.size());
+    rc |= upload(&h->faces, host->faces, (size_t)host->n_faces * 3);
+    rc |= upload(&h->coll_mask, mask.data(), mask.size());
+    h->n_faces = host->n_faces;
+    if (rc) {
+        dsf_mano_free(h);
+        return DSF_ERR_CUDA;
+    }
+    *out = h;
+    return DSF_OK;
+}
+
+extern "C" int dsf_mano_free(DsfMano* h) {
+    if (!h) return DSF_OK;
+    void* ptrs[] = {h->Dmat, h->DmatT, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
+                    h->jr_ptr, h->jr_idx, h->jr_w, h->faces, h->coll_mask};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    free(h);
+    return DSF_OK;
+}
+
+extern "C" long dsf_mano_workspace_floats(int batch) { return (long)batch * WS_PER_HAND; }
+extern "C" const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces) {
+    if (!h) return nullptr;
+    if (n_faces) *n_faces = h->n_faces;
+    return h->faces;
+}
+
+static ChainTopo topo_of(const DsfMano* h) {
+    ChainTopo t;
+    for (int i = 0; i < NJ; ++i) {
+        t.parents[i] = h->parents[i];
+        t.level[i] = h->level[i];
+    }
+    t.maxlevel = h->maxlevel;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: pose kernel - 16 lanes per hand, lane j owns joint j.
+//   PCA pose -> axis angles (mano_layer.py:601), Rodrigues (:720-728), pose feature (:611),
+//   rest joints from beta (:586-591), kinematic chain by tree level (:730-770).
+// ------------------------------------------------------------------------------------------------
+#define POSE_HPB 8   // hands per block (128 threads)
+
+__global__ void __launch_bounds__(POSE_HPB* NJ)
+mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const float* __restrict__ mean,
+                 const float* __restrict__ Jt, const float* __restrict__ JS, ChainTopo topo,
+                 float* __restrict__ ws) {
+    __shared__ float s_theta[POSE_HPB][48];
+    __shared__ float s_beta[POSE_HPB][12];
+    __shared__ float s_G[POSE_HPB][NJ][15];   // Gr[9] Gt[3] J[3]
+    const int hl = threadIdx.x / NJ;
+    const int j = threadIdx.x % NJ;
+    const int hand = blockIdx.x * POSE_HPB + hl;
+    const bool live = hand < B;
+    const int hh = live ? hand : B - 1;
+
+    for (int k = j; k < 45; k += NJ) s_theta[hl][k] = (k < p.ncomp) ? p.theta[(size_t)hh * p.ld_theta + k] : 0.f;
+    if (j < 10) s_beta[hl][j] = p.beta[(size_t)hh * p.ld_beta + j];
+    __syncwarp();
+
+    float ang[3] = {0.f, 0.f, 0.f};
+    float R[9];
+    if (j == 0) {
+        if (p.quat_dim == 3) {
+            ang[0] = p.quat[(size_t)hh * p.ld_quat];
+            ang[1] = p.quat[(size_t)hh * p.ld_quat + 1];
+            ang[2] = p.quat[(size_t)hh * p.ld_quat + 2];
+            rodrigues(ang, R);
+        } else {
+            float q[4];
+            for (int i = 0; i < 4; ++i) q[i] = p.quat[(size_t)hh * p.ld_quat + i];
+            quat_to_mat(q, R, nullptr, nullptr);
+        }
+    } else {
+        const int a0 = 3 * (j - 1);
+        ang[0] = mean[a0]; ang[1] = mean[a0 + 1]; ang[2] = mean[a0 + 2];
+        for (int k = 0; k < p.ncomp; ++k) {
+            float t = s_theta[hl][k];
+            ang[0] = fmaf(t, __ldg(comp + k * 45 + a0), ang[0]);
+            ang[1] = fmaf(t, __ldg(comp + k * 45 + a0 + 1), ang[1]);
+            ang[2] = fmaf(t, __ldg(comp + k * 45 + a0 + 2), ang[2]);
+        }
+        rodrigues(ang, R);
+    }
+    float J[3] = {Jt[j * 3], Jt[j * 3 + 1], Jt[j * 3 + 2]};
+#pragma unroll
+    for (int b = 0; b < 10; ++b) {
+        float be = s_beta[hl][b];
+        J[0] = fmaf(be, __ldg(JS + (b * NJ + j) * 3), J[0]);
+        J[1] = fmaf(be, __ldg(JS + (b * NJ + j) * 3 + 1), J[1]);
+        J[2] = fmaf(be, __ldg(JS + (b * NJ + j) * 3 + 2), J[2]);
+    }
+    float* wsh = ws + (size_t)hh * WS_PER_HAND;
+    if (live) {
+        // GEMM operand row X = [beta | Rs - I | 0]
+        float* X = wsh + WS_X;
+        if (j < 10) X[j] = s_beta[hl][j];
+        if (j >= 1) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) X[10 + 9 * (j - 1) + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        }
+        if (j < KP - 145) X[145 + j] = 0.f;
+    }
+
+    float Gr[9], Gt[3];
+    if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Gr[e] = R[e];
+        Gt[0] = J[0]; Gt[1] = J[1]; Gt[2] = J[2];
+    }
+    s_G[hl][j][12] = J[0]; s_G[hl][j][13] = J[1]; s_G[hl][j][14] = J[2];
+    if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) s_G[hl][0][e] = Gr[e];
+        s_G[hl][0][9] = Gt[0]; s_G[hl][0][10] = Gt[1]; s_G[hl][0][11] = Gt[2];
+    }
+    __syncwarp();
+    for (int lvl = 1; lvl <= topo.maxlevel; ++lvl) {
+        if (topo.level[j] == lvl) {
+            const float* P = s_G[hl][topo.parents[j]];
+            float d[3] = {J[0] - P[12], J[1] - P[13], J[2] - P[14]};
+            mat3_mul(P, R, Gr);
+            mat3_vec(P, d, Gt);
+            Gt[0] += P[9]; Gt[1] += P[10]; Gt[2] += P[11];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) s_G[hl][j][e] = Gr[e];
+            s_G[hl][j][9] = Gt[0]; s_G[hl][j][10] = Gt[1]; s_G[hl][j][11] = Gt[2];
+        }
+        __syncwarp();
+    }
+    if (live) {
+        float* o = wsh + WS_RJ + j * RJ_STRIDE;
+        float GJ[3];
+        mat3_vec(Gr, J, GJ);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { o[RJ_R + e] = R[e]; o[RJ_GR + e] = Gr[e]; }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            o[RJ_GT + e] = Gt[e];
+            o[RJ_J + e] = J[e];
+            o[RJ_AT + e] = Gt[e] - GJ[e];   // A = G - [0 | G.J]  (mano_layer.py:765-768)
+            o[RJ_ANG + e] = ang[e];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: fp32 SIMT GEMM  C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]); all leading dims multiples of 4.
+// Used for the blend-shape contraction (:586,:613) and its transpose in backward.
+// ------------------------------------------------------------------------------------------------
+#define GB_M 64
+#define GB_N 64
+#define GB_K 16
+
+__global__ void __launch_bounds__(256)
+sgemm_bias_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
+                  int ldb, float* __restrict__ C, int ldc, const float* __restrict__ bias) {
+    __shared__ float As[GB_K][GB_M + 4];
+    __shared__ float Bs[GB_K][GB_N + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+    const int tr = tid / 16, tc = tid % 16;     // 16x16 threads, 4x4 outputs each
+    float acc[4][4] = {};
+    const int a_row = tid / 4, a_k4 = (tid % 4) * 4;        // A tile: 64 rows x 16 k
+    const int b_k = tid / 16, b_n4 = (tid % 16) * 4;        // B tile: 16 k x 64 cols
+    for (int k0 = 0; k0 < K; k0 += GB_K) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        if (m0 + a_row < M && k0 + a_k4 < K)
+            av = *reinterpret_cast<const float4*>(A + (size_t)(m0 + a_row) * lda + k0 + a_k4);
+        if (k0 + b_k < K && n0 + b_n4 < N)
+            bv = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + b_k) * ldb + n0 + b_n4);
+        As[a_k4][a_row] = av.x; As[a_k4 + 1][a_row] = av.y; As[a_k4 + 2][a_row] = av.z; As[a_k4 + 3][a_row] = av.w;
+        *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GB_K; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][tr * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tc * 4]);
+            float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(ar[i], br[jn], acc[i][jn]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tc * 4;
+    if (n < N) {
+        float4 bz = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m = m0 + tr * 4 + i;
+            if (m < M)
+                *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) =
+                    make_float4(acc[i][0] + bz.x, acc[i][1] + bz.y, acc[i][2] + bz.z, acc[i][3] + bz.w);
+        }
+    }
+}
+
+static int launch_sgemm(int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, float* C,
+                        int ldc, const float* bias, cudaStream_t st) {
+    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
+    sgemm_bias_kernel<<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, bias);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: skinning kernel - one CTA per hand.  LBS (:619-629), joint regression (:630-633), wrist-cap
+// vertex (:636-637), unit / camera scaling (:662-675).
+// ------------------------------------------------------------------------------------------------
+#define SKIN_T 128
+static const int h_ring[16] = {121, 214, 215, 279, 239, 234, 92, 38, 122, 118, 117, 119, 120, 108, 79, 78};
+static const int h_tips[5] = {333, 444, 672, 555, 744};
+__constant__ int c_ring[16];
+__constant__ int c_tips[5];
+static bool g_const_ready[16] = {};
+
+static int ensure_constants() {
+    int dev = 0;
+    DSF_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 16 && g_const_ready[dev]) return DSF_OK;
+    DSF_CHECK_CUDA(cudaMemcpyToSymbol(c_ring, h_ring, sizeof(h_ring)));
+    DSF_CHECK_CUDA(cudaMemcpyToSymbol(c_tips, h_tips, sizeof(h_tips)));
+    if (dev < 16) g_const_ready[dev] = true;
+    return DSF_OK;
+}
+
+__global__ void __launch_bounds__(SKIN_T)
+mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ W,
+                 const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
+                 const float* __restrict__ jr_w, const float* __restrict__ cam, int ld_cam, float unit_scale,
+                 float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ Rs) {
+    __shared__ float sA[NJ][12];
+    __shared__ float sV[NVW * 3];
+    const int hand = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* wsh = ws + (size_t)hand * WS_PER_HAND;
+    for (int i = tid; i < NJ * 12; i += SKIN_T) {
+        int j = i / 12, e = i % 12;
+        sA[j][e] = (e < 9) ? wsh[WS_RJ + j * RJ_STRIDE + RJ_GR + e] : wsh[WS_RJ + j * RJ_STRIDE + RJ_AT + e - 9];
+    }
+    if (Rs) {
+        for (int i = tid; i < 15 * 9; i += SKIN_T)
+            Rs[(size_t)hand * 135 + i] = wsh[WS_RJ + (1 + i / 9) * RJ_STRIDE + RJ_R + i % 9];
+    }
+    float s = unit_scale, tx = 0.f, ty = 0.f, tz = 0.f;
+    if (cam) {
+        s *= cam[(size_t)hand * ld_cam];
+        tx = cam[(size_t)hand * ld_cam + 1];
+        ty = cam[(size_t)hand * ld_cam + 2];
+        tz = cam[(size_t)hand * ld_cam + 3];
+    }
+    __syncthreads();
+    const float* VP = wsh + WS_VP;
+    float* vo = verts + (size_t)hand * NVW * 3;
+    for (int v = tid; v < NV; v += SKIN_T) {
+        float x = VP[3 * v], y = VP[3 * v + 1], z = VP[3 * v + 2];
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(W + v * NJ);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 w4 = __ldg(wp + q);
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (wv[i] != 0.f) {
+                    const float* Aj = sA[q * 4 + i];
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) T[e] = fmaf(wv[i], Aj[e], T[e]);
+                }
+            }
+        }
+        float ox = T[0] * x + T[1] * y + T[2] * z + T[9];
+        float oy = T[3] * x + T[4] * y + T[5] * z + T[10];
+        float oz = T[6] * x + T[7] * y + T[8] * z + T[11];
+        sV[3 * v] = ox; sV[3 * v + 1] = oy; sV[3 * v + 2] = oz;
+        vo[3 * v] = ox * s + tx; vo[3 * v + 1] = oy * s + ty; vo[3 * v + 2] = oz * s + tz;
+    }
+    __syncthreads();
+    const int warp = tid / 32, lane = tid % 32;
+    if (warp == 0) {   // wrist-cap centre = mean of the 16 ring vertices
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (lane < 16) { int r = c_ring[lane]; a = sV[3 * r]; b = sV[3 * r + 1]; c = sV[3 * r + 2]; }
+        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+        if (lane == 0) {
+            a *= (1.f / 16.f); b *= (1.f / 16.f); c *= (1.f / 16.f);
+            vo[3 * NV] = a * s + tx; vo[3 * NV + 1] = b * s + ty; vo[3 * NV + 2] = c * s + tz;
+        }
+    }
+    float* jo = joints + (size_t)hand * NJOUT * 3;
+    for (int j = warp; j < NJ; j += SKIN_T / 32) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int e = jr_ptr[j] + lane; e < jr_ptr[j + 1]; e += 32) {
+            int v = jr_idx[e];
+            float w = jr_w[e];
+            a = fmaf(w, sV[3 * v], a); b = fmaf(w, sV[3 * v + 1], b); c = fmaf(w, sV[3 * v + 2], c);
+        }
+        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+        if (lane == 0) { jo[3 * j] = a * s + tx; jo[3 * j + 1] = b * s + ty; jo[3 * j + 2] = c * s + tz; }
+    }
+    if (tid < 5) {
+        int v = c_tips[tid];
+        jo[3 * (NJ + tid)] = sV[3 * v] * s + tx;
+        jo[3 * (NJ + tid) + 1] = sV[3 * v + 1] * s + ty;
+        jo[3 * (NJ + tid) + 2] = sV[3 * v + 2] * s + tz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kb2: skinning backward - one CTA per hand.
+//   cotangents of verts/joints -> g_vposed (ws), g_A (ws), g_cam.
+// ------------------------------------------------------------------------------------------------
+#define SKB_T 128
+#define SKB_VPT ((NV + SKB_T - 1) / SKB_T)   // 7 vertices per thread
+
+__global__ void __launch_bounds__(SKB_T)
+mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
+                     const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
+                     const float* __restrict__ jr_w, const float* __restrict__ cam, int ld_cam,
+                     float unit_scale, const float* __restrict__ verts, const float* __restrict__ joints,
+                     const float* __restrict__ g_verts, const float* __restrict__ g_joints,
+                     float* __restrict__ g_cam, int ld_gcam) {
+    __shared__ float sg[NVW * 3];
+    __shared__ float sGr[NJ][9];
+    __shared__ float sgj[NJOUT * 3];
+    __shared__ float red[SKB_T / 32][12];
+    const int hand = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    float* wsh = ws + (size_t)hand * WS_PER_HAND;
+    float cs = 1.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    if (cam) {
+        cs = cam[(size_t)hand * ld_cam];
+        tx = cam[(size_t)hand * ld_cam + 1];
+        ty = cam[(size_t)hand * ld_cam + 2];
+        tz = cam[(size_t)hand * ld_cam + 3];
+    }
+    const float s_tot = unit_scale * cs;
+    for (int i = tid; i < NJ * 9; i += SKB_T) sGr[i / 9][i % 9] = wsh[WS_RJ + (i / 9) * RJ_STRIDE + RJ_GR + i % 9];
+    for (int i = tid; i < NJOUT * 3; i += SKB_T) sgj[i] = g_joints ? g_joints[(size_t)hand * NJOUT * 3 + i] : 0.f;
+    // camera gradient partials: out = mano * s_tot + t
+    float pt[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* gv = g_verts ? g_verts + (size_t)hand * NVW * 3 : nullptr;
+    const float* vo = verts + (size_t)hand * NVW * 3;
+    for (int v = tid; v < NVW; v += SKB_T) {
+        float a = gv ? gv[3 * v] : 0.f, b = gv ? gv[3 * v + 1] : 0.f, c = gv ? gv[3 * v + 2] : 0.f;
+        sg[3 * v] = a; sg[3 * v + 1] = b; sg[3 * v + 2] = c;
+        pt[1] += a; pt[2] += b; pt[3] += c;
+        pt[0] += a * (vo[3 * v] - tx) + b * (vo[3 * v + 1] - ty) + c * (vo[3 * v + 2] - tz);
+    }
+    __syncthreads();
+    if (tid < NJOUT) {
+        const float* jo = joints + (size_t)hand * NJOUT * 3 + 3 * tid;
+        float a = sgj[3 * tid], b = sgj[3 * tid + 1], c = sgj[3 * tid + 2];
+        pt[1] += a; pt[2] += b; pt[3] += c;
+        pt[0] += a * (jo[0] - tx) + b * (jo[1] - ty) + c * (jo[2] - tz);
+    }
+    // wrist-cap vertex spreads onto the ring (:636)
+    if (tid < 16) {
+        int r = c_ring[tid];
+        sg[3 * r] += sg[3 * NV] * (1.f / 16.f);
+        sg[3 * r + 1] += sg[3 * NV + 1] * (1.f / 16.f);
+        sg[3 * r + 2] += sg[3 * NV + 2] * (1.f / 16.f);
+    }
+    __syncthreads();
+    if (tid < 5) {
+        int v = c_tips[tid];
+        sg[3 * v] += sgj[3 * (NJ + tid)];
+        sg[3 * v + 1] += sgj[3 * (NJ + tid) + 1];
+        sg[3 * v + 2] += sgj[3 * (NJ + tid) + 2];
+    }
+    __syncthreads();
+    if (g_joints) {
+        for (int j = warp; j < NJ; j += SKB_T / 32) {
+            float a = sgj[3 * j], b = sgj[3 * j + 1], c = sgj[3 * j + 2];
+            for (int e = jr_ptr[j] + lane; e < jr_ptr[j + 1]; e += 32) {
+                int v = jr_idx[e];
+                float w = jr_w[e];
+                atomicAdd(&sg[3 * v], w * a);
+                atomicAdd(&sg[3 * v + 1], w * b);
+                atomicAdd(&sg[3 * v + 2], w * c);
+            }
+        }
+    }
+    __syncthreads();
+    // per-vertex: g_vposed = T^T g ; keep (g, vp) in registers for the g_A reduction
+    float rg[SKB_VPT][3], rv[SKB_VPT][3];
+    const float* VP = wsh + WS_VP;
+    float* GVP = wsh + WS_GVP;
+#pragma unroll
+    for (int i = 0; i < SKB_VPT; ++i) {
+        int v = tid + i * SKB_T;
+        if (v < NV) {
+            float g0 = sg[3 * v] * s_tot, g1 = sg[3 * v + 1] * s_tot, g2 = sg[3 * v + 2] * s_tot;
+            rg[i][0] = g0; rg[i][1] = g1; rg[i][2] = g2;
+            rv[i][0] = VP[3 * v]; rv[i][1] = VP[3 * v + 1]; rv[i][2] = VP[3 * v + 2];
+            float T[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) T[e] = 0.f;
+            for (int j = 0; j < NJ; ++j) {
+                float w = __ldg(W + v * NJ + j);
+                if (w != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) T[e] = fmaf(w, sGr[j][e], T[e]);
+                }
+            }
+            GVP[3 * v] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+            GVP[3 * v + 1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+            GVP[3 * v + 2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+        } else {
+            rg[i][0] = rg[i][1] = rg[i][2] = 0.f;
+            rv[i][0] = rv[i][1] = rv[i][2] = 0.f;
+        }
+    }
+    if (tid < NP - NV * 3) GVP[NV * 3 + tid] = 0.f;
+    // g_A[j] = sum_v w_vj [ g (x) vp | g ]
+    float* GA = wsh + WS_GA;
+    for (int j = 0; j < NJ; ++j) {
+        float acc[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < SKB_VPT; ++i) {
+            int v = tid + i * SKB_T;
+            float w = (v < NV) ? __ldg(W + v * NJ + j) : 0.f;
+            if (w != 0.f) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float wg = w * rg[i][r];
+                    acc[3 * r] = fmaf(wg, rv[i][0], acc[3 * r]);
+                    acc[3 * r + 1] = fmaf(wg, rv[i][1], acc[3 * r + 1]);
+                    acc[3 * r + 2] = fmaf(wg, rv[i][2], acc[3 * r + 2]);
+                    acc[9 + r] += wg;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) red[warp][e] = acc[e];
+        }
+        __syncthreads();
+        if (tid < 12) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < SKB_T / 32; ++w) a += red[w][tid];
+            GA[j * 12 + tid] = a;
+        }
+        __syncthreads();
+    }
+    // camera gradient
+    if (g_cam) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pt[e] = warp_sum(pt[e]);
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) red[warp][e] = pt[e];
+        }
+        __syncthreads();
+        if (tid < 4) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < SKB_T / 32; ++w) a += red[w][tid];
+            // d out / d cam.scale = unit_scale * mano = (out - t) / cam.scale
+            if (tid == 0) a = a / cs;
+            g_cam[(size_t)hand * ld_gcam + tid] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kb4: pose backward - 16 lanes per hand.  g_A, g_X -> g_quat, g_theta, g_beta.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POSE_HPB* NJ)
+mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __restrict__ comp,
+                     const float* __restrict__ JS, ChainTopo topo, const float* __restrict__ ws) {
+    __shared__ float s_acc[POSE_HPB][NJ][15];   // gGr[9] gGt[3] gJ[3]
+    __shared__ float s_gang[POSE_HPB][48];
+    const int hl = threadIdx.x / NJ;
+    const int j = threadIdx.x % NJ;
+    const int hand = blockIdx.x * POSE_HPB + hl;
+    const bool live = hand < B;
+    const int hh = live ? hand : B - 1;
+    const float* wsh = ws + (size_t)hh * WS_PER_HAND;
+    const float* rj = wsh + WS_RJ + j * RJ_STRIDE;
+    float R[9], Gr[9], J[3], ang[3];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { R[e] = rj[RJ_R + e]; Gr[e] = rj[RJ_GR + e]; }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { J[e] = rj[RJ_J + e]; ang[e] = rj[RJ_ANG + e]; }
+    const float* ga = wsh + WS_GA + j * 12;
+    float gAt[3] = {ga[9], ga[10], ga[11]};
+    // A_r = Gr, A_t = Gt - Gr J
+    float tmp[3];
+    mat3T_vec(Gr, gAt, tmp);
+    float* acc = s_acc[hl][j];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[3 * r + c] = ga[3 * r + c] - gAt[r] * J[c];
+    acc[9] = gAt[0]; acc[10] = gAt[1]; acc[11] = gAt[2];
+    acc[12] = -tmp[0]; acc[13] = -tmp[1]; acc[14] = -tmp[2];
+    __syncwarp();
+    float gR[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) gR[e] = 0.f;
+    for (int lvl = topo.maxlevel; lvl >= 1; --lvl) {
+        if (topo.level[j] == lvl) {
+            const int pj = topo.parents[j];
+            const float* prj = wsh + WS_RJ + pj * RJ_STRIDE;
+            float Pg[9], Pj[3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Pg[e] = prj[RJ_GR + e];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) Pj[e] = prj[RJ_J + e];
+            float gGr[9], gGt[3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) gGr[e] = acc[e];
+            gGt[0] = acc[9]; gGt[1] = acc[10]; gGt[2] = acc[11];
+            mat3T_mul(Pg, gGr, gR);                      // g_R_j = Gr_p^T g_Gr_j
+            float d[3] = {J[0] - Pj[0], J[1] - Pj[1], J[2] - Pj[2]};
+            float up[9];
+            mat3_mulT(gGr, R, up);                       // g_Gr_p += g_Gr_j R_j^T + g_Gt_j (x) d
+            float* pacc = s_acc[hl][pj];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(&pacc[3 * r + c], up[3 * r + c] + gGt[r] * d[c]);
+            float gd[3];
+            mat3T_vec(Pg, gGt, gd);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                atomicAdd(&pacc[9 + e], gGt[e]);
+                atomicAdd(&pacc[12 + e], -gd[e]);
+                atomicAdd(&acc[12 + e], gd[e]);
+            }
+        }
+        __syncwarp();
+    }
+    if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) gR[e] = acc[e];
+        acc[12] += acc[9]; acc[13] += acc[10]; acc[14] += acc[11];   // Gt_0 = J_0
+    }
+    // pose blend shapes: pose_feature = Rs - I
+    if (j >= 1) {
+        const float* gx = wsh + WS_GX + 10 + 9 * (j - 1);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) gR[e] += gx[e];
+    }
+    __syncwarp();
+    if (j == 0 && p.quat_dim == 4) {
+        float q[4], gq[4];
+        for (int i = 0; i < 4; ++i) q[i] = p.quat[(size_t)hh * p.ld_quat + i];
+        quat_to_mat_bwd(q, gR, gq);
+        if (live) for (int i = 0; i < 4; ++i) g.quat[(size_t)hh * g.ld_quat + i] = gq[i];
+    } else {
+        float gt[3];
+        rodrigues_bwd(ang, gR, gt);
+        if (j == 0) {
+            if (live) for (int i = 0; i < 3; ++i) g.quat[(size_t)hh * g.ld_quat + i] = gt[i];
+        } else {
+            s_gang[hl][3 * (j - 1)] = gt[0];
+            s_gang[hl][3 * (j - 1) + 1] = gt[1];
+            s_gang[hl][3 * (j - 1) + 2] = gt[2];
+        }
+    }
+    __syncwarp();
+    if (live) {
+        for (int k = j; k < p.ncomp; k += NJ) {       // angles = theta . comp[:ncomp] + mean
+            float a = 0.f;
+            for (int c = 0; c < 45; ++c) a = fmaf(__ldg(comp + k * 45 + c), s_gang[hl][c], a);
+            g.theta[(size_t)hh * g.ld_theta + k] = a;
+        }
+        if (j < 10) {                                  // direct blend-shape term + rest-joint term
+            float a = wsh[WS_GX + j];
+            for (int i = 0; i < NJ; ++i) {
+                const float* gj = &s_acc[hl][i][12];
+                const float* js = JS + (j * NJ + i) * 3;
+                a += __ldg(js) * gj[0] + __ldg(js + 1) * gj[1] + __ldg(js + 2) * gj[2];
+            }
+            g.beta[(size_t)hh * g.ld_beta + j] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// entry points
+// ------------------------------------------------------------------------------------------------
+static int check_params(const DsfManoParams* p) {
+    DSF_REQUIRE(p && p->quat && p->theta && p->beta, "null parameter pointers");
+    DSF_REQUIRE(p->quat_dim == 3 || p->quat_dim == 4, "quat_dim must be 3 or 4");
+    DSF_REQUIRE(p->ncomp >= 0 && p->ncomp <= 45, "ncomp must be in [0,45]");
+    return DSF_OK;
+}
+
+int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale, float* verts,
+                          float* joints, float* Rs, float* ws, cudaStream_t st) {
+    int rc = ensure_constants();
+    if (rc) return rc;
+    ChainTopo topo = topo_of(h);
+    mano_pose_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, h->comp, h->mean, h->Jt,
+                                                                              h->JS, topo, ws);
+    DSF_CHECK_LAUNCH();
+    // v_posed = v_template + [beta | Rs - I] . [shapedirs ; posedirs]
+    rc = launch_sgemm(B, NP, KP, ws + WS_X, WS_PER_HAND, h->Dmat, NP, ws + WS_VP, WS_PER_HAND, h->vt, st);
+    if (rc) return rc;
+    mano_skin_kernel<<<B, SKIN_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
+                                           unit_scale, verts, joints, Rs);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale,
+                           const float* verts, const float* joints, const float* g_verts,
+                           const float* g_joints, const DsfManoGrads* g, float* ws, cudaStream_t st) {
+    int rc = ensure_constants();
+    if (rc) return rc;
+    ChainTopo topo = topo_of(h);
+    mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
+                                              unit_scale, verts, joints, g_verts, g_joints,
+                                              p->cam ? g->cam : nullptr, g->ld_cam);
+    DSF_CHECK_LAUNCH();
+    // g_X = g_vposed . Dmat^T
+    rc = launch_sgemm(B, KP, NP, ws + WS_GVP, WS_PER_HAND, h->DmatT, KP, ws + WS_GX, WS_PER_HAND, nullptr, st);
+    if (rc) return rc;
+    mano_pose_bwd_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, *g, h->comp, h->JS,
+                                                                                  topo, ws);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+extern "C" int dsf_mano_forward(const DsfMano* h, int batch, const DsfManoParams* p, float unit_scale,
+                                float* verts, float* joints, float* Rs, float* workspace,
+                                dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && verts && joints && workspace, "null handle/output/workspace");
+    DSF_REQUIRE(batch > 0, "batch must be positive");
+    int rc = check_params(p);
+    if (rc) return rc;
+    return dsf_mano_forward_impl(h, batch, p, unit_scale, verts, joints, Rs, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParams* p, float unit_scale,
+                                 const float* verts, const float* joints, const float* g_verts,
+                                 const float* g_joints, const DsfManoGrads* g, float* workspace,
+                                 dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && verts && joints && workspace && g, "null handle/input/workspace");
+    DSF_REQUIRE(batch > 0, "batch must be positive");
+    DSF_REQUIRE(g->quat && g->theta && g->beta, "null gradient outputs");
+    DSF_REQUIRE(!p || !p->cam || g->cam, "cam given but g.cam is null");
+    int rc = check_params(p);
+    if (rc) return rc;
+    return dsf_mano_backward_impl(h, batch, p, unit_scale, verts, joints, g_verts, g_joints, g, workspace,
+                                  (cudaStream_t)stream);
+}

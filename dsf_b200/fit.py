@@ -1,0 +1,94 @@
+"""Fused model-fitting step (dsf_fit_step): MANO forward -> rasterise -> m2d depth loss -> backward
+to the 62 MANO/camera parameters, with persistent buffers and optional CUDA-graph replay.
+
+This is the unit bench.py times: one call = one pass of the hot path over one batch of hands.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class FitStep:
+    def __init__(self, mano_layer, batch, crop=128, cam_para=(588.03, 587.07, 320.0, 240.0),
+                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None):
+        self.lib = L.lib()
+        self.layer = mano_layer
+        self.B, self.R = int(batch), int(crop)
+        self.mode = 0 if mode == "direct" else 1
+        self.loss_weight = float(loss_weight)
+        self.dev = device or mano_layer.v_template.device
+        self.W, self.H = int(image_size[0]), int(image_size[1])
+        self._intr = (C.c_float * 4)(*[float(v) for v in cam_para])
+        B, R, dev = self.B, self.R, self.dev
+        f = lambda *s: torch.empty(*s, device=dev)
+        self.params = f(B, 62)
+        self.center3d = f(B, 3)
+        self.cube = f(B, 3)
+        self.target = f(B, R, R)
+        self.view = f(B, L.VIEW_STRIDE)
+        self.xs = f(B, R)
+        self.ys = f(B, R)
+        self.M = f(B, 3, 3)
+        self.img = f(B, R, R)
+        self.p2f = torch.empty(B, R, R, dtype=torch.int32, device=dev)
+        self.verts = f(B, L.NVW, 3)
+        self.joints = f(B, L.NJOUT, 3)
+        self.g_params = f(B, 62)
+        self.parts = f(B, 2)
+        self.totals = f(4)
+        self.ws = f(self.lib.dsf_fit_workspace_floats(B, R))
+        self.use_graph = use_graph
+        self._graph = None
+        self.launches_per_step = 0
+
+    # inputs already resident in HBM -----------------------------------------------------------------
+    def set_inputs(self, params, center3d, cube, target=None):
+        self.params.copy_(params, non_blocking=True)
+        self.center3d.copy_(center3d, non_blocking=True)
+        self.cube.copy_(cube, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
+
+    def _enqueue(self):
+        s = L.stream_ptr()
+        n = 0
+        L.check(self.lib.dsf_view_setup(self.mode, self.B, self.center3d.data_ptr(), self.cube.data_ptr(),
+                                        self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
+                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), s))
+        n += self.lib.dsf_last_launch_count()
+        L.check(self.lib.dsf_fit_step(self.layer._handle, self.B, self.R, self.params.data_ptr(),
+                                      self.center3d.data_ptr(), self.cube.data_ptr(), self.view.data_ptr(),
+                                      self.xs.data_ptr(), self.ys.data_ptr(), self.target.data_ptr(),
+                                      self.loss_weight, self.img.data_ptr(), self.p2f.data_ptr(),
+                                      self.verts.data_ptr(), self.joints.data_ptr(), self.g_params.data_ptr(),
+                                      self.parts.data_ptr(), self.totals.data_ptr(), self.ws.data_ptr(), s))
+        n += self.lib.dsf_last_launch_count()
+        self.launches_per_step = n
+
+    def step(self):
+        """Enqueue one fitting step on the current stream; results stay on the device
+        (self.totals[0] = loss, self.g_params = d loss / d params, self.img = rendered depth)."""
+        if not self.use_graph:
+            self._enqueue()
+            return
+        if self._graph is None:
+            self._enqueue()                      # warm-up outside capture (lazy module load, attributes)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self._graph = g
+        self._graph.replay()
+
+    def render_target(self, params_target):
+        """Fill self.target with the rendering of another parameter set (synthetic 'real' depth)."""
+        keep = self.params.clone()
+        self.params.copy_(params_target)
+        self.target.fill_(1.0)
+        self._enqueue()
+        self.target.copy_(self.img)
+        self.params.copy_(keep)

@@ -1,0 +1,177 @@
+/* dsf_b200 - C ABI of the B200-native DSF model-fitting hot path (libdsf_b200.so).
+ *
+ * Every entry point: plain pointers and sizes, no torch types, returns 0 on success or a
+ * negative DsfStatus; never throws, never allocates per call (except dsf_mano_create), never
+ * synchronises the device; work is enqueued on the cudaStream_t passed last (a CUstream /
+ * torch.cuda.current_stream().cuda_stream handle).  All tensors are fp32 row-major and owned
+ * by the caller; indices are int32.  Re-entrant; the only library-owned state is the constant
+ * set behind a DsfMano handle.  CUDA-graph capturable.
+ *
+ * Each declaration names the reference interface it replaces (paths relative to the DSF repo).
+ */
+#ifndef DSF_B200_H
+#define DSF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dsfStream_t; /* cudaStream_t */
+
+enum DsfStatus {
+    DSF_OK = 0,
+    DSF_ERR_BAD_ARG = -1,
+    DSF_ERR_CUDA = -2,
+    DSF_ERR_UNSUPPORTED = -3,
+    DSF_ERR_NO_DEVICE = -4
+};
+
+#define DSF_NV 778        /* MANO vertices */
+#define DSF_NVW 779       /* + wrist-cap centre (mano_layer.py:636-637) */
+#define DSF_NJ 16         /* kinematic joints */
+#define DSF_NJOUT 21      /* + 5 fingertip vertices (mano_layer.py:124-131) */
+#define DSF_NBETA 10
+#define DSF_NPOSE 135
+#define DSF_NSPHERE 66
+#define DSF_VIEW_STRIDE 16 /* floats per hand in a view record, see dsf_view_setup */
+
+const char* dsf_last_error_string(void);
+int dsf_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * M0  MANO constants  - replaces MANO_SMPL.__init__ buffer set-up, render_model/mano_layer.py:98-269
+ * Host arrays in the layouts the reference builds; copied to the current device once. */
+typedef struct DsfManoHost {
+    const float* v_template;  /* (778,3)                       :112-113 */
+    const float* shapedirs;   /* (10,2334)  reshape(-1,10).T   :116-120 */
+    const float* posedirs;    /* (135,2334)                    :142-145 */
+    const float* j_regressor; /* (778,16)   regressed joints   :123 (tip columns are implied) */
+    const float* hands_comp;  /* (45,45)                       :135-136 */
+    const float* hands_mean;  /* (45)                          :138-139 */
+    const float* weights;     /* (778,16)                      :149-154 */
+    const int* parents;       /* (16) parents[0] ignored       :147 */
+    const int* faces;         /* (n_faces,3) incl. the 16 wrist-fan faces :102-106 */
+    int n_faces;
+} DsfManoHost;
+
+typedef struct DsfMano DsfMano;
+int dsf_mano_create(const DsfManoHost* host, DsfMano** out);
+int dsf_mano_free(DsfMano* h);
+/* floats of caller-provided scratch per call of dsf_mano_forward (kept for dsf_mano_backward) */
+long dsf_mano_workspace_floats(int batch);
+
+/* A (B, ...) parameter block addressed with row strides so the slices of a (B,62) tensor
+ * (mano_layer.py:1073-1076) can be passed without copies. cam may be NULL (raw MANO metres). */
+typedef struct DsfManoParams {
+    const float* quat;  int ld_quat;  int quat_dim; /* 3 axis-angle or 4 quaternion (w,x,y,z) */
+    const float* theta; int ld_theta; int ncomp;    /* PCA coefficients, ncomp <= 45 */
+    const float* beta;  int ld_beta;                /* 10 */
+    const float* cam;   int ld_cam;                 /* (scale, tx, ty, tz) or NULL */
+} DsfManoParams;
+
+typedef struct DsfManoGrads {
+    float* quat;  int ld_quat;
+    float* theta; int ld_theta;
+    float* beta;  int ld_beta;
+    float* cam;   int ld_cam;   /* may be NULL when params.cam is NULL */
+} DsfManoGrads;
+
+/* M1-M4  replaces MANO_SMPL.forward (mano_layer.py:573-641) and get_mano_vertices (:643-678).
+ * verts (B,779,3), joints (B,21,3), Rs (B,15,3,3) or NULL.
+ * With cam: out = (mano * unit_scale) * cam.scale + cam.trans, unit_scale = 1000 [* global_scale].
+ * Without cam: unit_scale is applied alone (pass 1 for MANO_SMPL.forward). */
+int dsf_mano_forward(const DsfMano* h, int batch, const DsfManoParams* p, float unit_scale,
+                     float* verts, float* joints, float* Rs, float* workspace, dsfStream_t stream);
+
+/* autograd of the above: cotangents g_verts (B,779,3) / g_joints (B,21,3) (either may be NULL)
+ * -> parameter gradients (overwritten).  workspace must be the one forward filled;
+ * verts/joints are forward's outputs. */
+int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParams* p, float unit_scale,
+                      const float* verts, const float* joints, const float* g_verts,
+                      const float* g_joints, const DsfManoGrads* g, float* workspace,
+                      dsfStream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R0/R3  per-hand camera + crop set-up - replaces Render.points3DToImg / comToBounds /
+ * Offset2Trans / resize / affine_grid (mano_layer.py:1318-1324, :1133-1169, :1233-1260) and
+ * the pytorch3d PerspectiveCameras / RasterizationSettings built at :939-952.
+ * mode 0 "direct": R x R raster with crop-space intrinsics, samples at crop pixel centres.
+ * mode 1 "literal": the S x S raster -> (H,W) resize -> crop chain, evaluated only at the
+ *         raster pixel each crop pixel reads (S = max(W,H)); M_in (B,3,3) optional (M_render /
+ *         getDepth pass their own, must be axis-aligned), else recomputed like render() does.
+ * Outputs: view (B,16) = [fxn,fyn,pxn,pyn, zc,zhalf,bg, ax,bx,ay,by, x_lo,x_hi,y_lo,y_hi(as float), 0],
+ *          xs (B,R), ys (B,R) NDC sample coordinates (NaN = reads zero padding), M_out (B,3,3) or NULL. */
+int dsf_view_setup(int mode, int batch, const float* center3d, const float* cube,
+                   const float* intr4, int W, int H, int R, const float* M_in, float* view,
+                   float* xs, float* ys, float* M_out, dsfStream_t stream);
+
+/* R1/R4  replaces self.rasterizer(meshes) (mano_layer.py:1083, pytorch3d 0.4.0
+ * _C.rasterize_meshes, faces_per_pixel=1, blur_radius=0, perspective-correct) fused with the
+ * background fill (:1084-1085) and normalize_img (:1289-1299).
+ * verts_cam (NM,779,3) camera-space mm; faces come from the handle.
+ * img (NM,R,R) normalised depth; pix_to_face (NM,R,R) int32 (-1 bg, index local to the mesh);
+ * optional Fragments outputs zbuf (NM,R,R), bary (NM,R,R,3), dists (NM,R,R) with -1 background. */
+int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
+                       const float* xs, const float* ys, int R, float* img, int* pix_to_face,
+                       float* zbuf, float* bary, float* dists, dsfStream_t stream);
+
+/* R2  replaces _C.rasterize_meshes_backward + the index_put to verts + the camera chain, for
+ * the zbuf-only gradient DSF uses.  g_img (NM,R,R) is the cotangent of img.
+ * g_verts_cam (NM,779,3) overwritten. */
+int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
+                        const float* xs, const float* ys, int R, const int* pix_to_face,
+                        const float* g_img, float* g_verts_cam, dsfStream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1/L2  render losses.
+ * mode 0: inline m2d loss, train_render.py:728-732  (union mask, per-hand normalised, x weight/B)
+ * mode 1: depth_loss.forward, render_model/render_loss.py:15-21 (both < thr, global mean)
+ * real/synth (B,R,R).  parts (B,2) = per-hand [sum |d|*mask, count]; totals (4) =
+ * [loss, sum, count, 0]; g_synth (B,R,R) or NULL = d loss / d synth. */
+int dsf_depth_loss(int mode, int batch, int R, const float* real, const float* synth, float thr,
+                   float weight, float* parts, float* totals, float* g_synth, dsfStream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C1  replaces MANO_SMPL.calculate_coll + get_sphere_radius (mano_layer.py:271-317, :373-385).
+ * joints (B,21,3), mesh (B,779,3) (treated as constant, every caller detaches it).
+ * out_loss (1) = mean over (B,66) of gated row sums; per_hand (B,2) = [ungated total, gated total];
+ * g_joints (B,21,3) or NULL = d out_loss / d joints.  NB the reference's 0.1 gate acts per sphere
+ * row (mano_layer.py:383 sums a size-1 axis), reproduced here. */
+int dsf_coll_forward_backward(const DsfMano* h, int batch, const float* joints, const float* mesh,
+                              float* out_loss, float* per_hand, float* g_joints,
+                              dsfStream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P1  replaces pytorch3d _C.point_face_dist_forward / _backward as wrapped by
+ * metric/meshLoss.py:21-70 and used by ICPLoss (:347-353) / JointICPLoss (:377-394), with the
+ * batch-shared face list DSF always passes.  points (B,P,3), verts (B,V,3),
+ * faces (F,3) int32 device pointer -> dists (B,P) squared, idxs (B,P) face index in its mesh. */
+int dsf_point_face_forward(int batch, int P, int V, int F, const float* points, const float* verts,
+                           const int* faces, float* dists, int* idxs, dsfStream_t stream);
+int dsf_point_face_backward(int batch, int P, int V, int F, const float* points, const float* verts,
+                            const int* faces, const int* idxs, const float* g_dists,
+                            float* g_points, float* g_verts, dsfStream_t stream);
+
+/* device pointer to the handle's face list (n_faces,3) int32, for dsf_point_face_* */
+const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused fitting step: M1+M4 -> R1/R4 -> L2 -> R2 -> MANO backward, one call, fixed launch
+ * sequence (graph-capturable).  params (B,62) = [quat3|theta45|beta10|scale|trans3]; target
+ * (B,R,R) normalised depth; view/xs/ys from dsf_view_setup; cube (B,3), center3d (B,3).
+ * Outputs: img (B,R,R), pix_to_face (B,R,R), verts (B,779,3), joints (B,21,3) (normalised cube
+ * units, global_scale 1/125), g_params (B,62) = d loss/d params, parts (B,2), totals (4). */
+long dsf_fit_workspace_floats(int batch, int R);
+int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
+                 const float* cube, const float* view, const float* xs, const float* ys,
+                 const float* target, float loss_weight, float* img, int* pix_to_face,
+                 float* verts, float* joints, float* g_params, float* parts, float* totals,
+                 float* workspace, dsfStream_t stream);
+
+/* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
+int dsf_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSF_B200_H */
