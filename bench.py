@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the DSF model-fitting hot path (contract: see the task's bench.py section).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One step = one pass of the hot path over one batch of synthetic hands: MANO forward ->
+depth rasterisation (128x128) -> m2d depth loss -> backward to the 62 MANO/camera parameters.
+Workload: BASELINE.json configs[2] ("large-batch render-loss fwd/bwd: batch 4096, 128x128"), 4096
+hands per GPU; under torchrun every rank owns its own 4096 hands (weak scaling, no data-path
+collective; one 16-byte all-reduce of the packed loss record per step).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hand fits/sec (MANO+raster+loss fwd/bwd)"
+UNIT = "fits/s"
+CROP = 128
+# algorithmic bytes per hand-fit at R=128, 1 view
+BYTES_PER_FIT = 2 * CROP * CROP * 4 + 779 * 3 * 4 + 21 * 3 * 4 + 62 * 4 + 62 * 4 + 4 + 60   # 141 232
+# the rasteriser kernel alone: reads verts + view/sample grids, writes normalised depth + pix_to_face
+RASTER_BYTES_PER_HAND = 779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 2 * CROP * CROP * 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if "Active" == r[2 + i]
+                          or r[2 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline (the oracle port of the reference's CPU path)
+# --------------------------------------------------------------------------------------------------
+def cpu_pipeline(batch: int, seed: int = 0):
+    from dsf_b200 import make_synthetic_mano, sample_fit_inputs
+    from oracle import mano_oracle as mo
+    from oracle import pipeline as pl
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    consts = mo.ManoConstants(make_synthetic_mano(0))
+    inp = {k: torch.from_numpy(v) for k, v in sample_fit_inputs(batch, seed=seed).items()}
+    with torch.no_grad():
+        target, *_ = pl.render(consts, inp["params_target"], inp["center3d"], inp["cube"])
+    target = target.detach()
+
+    def step():
+        return pl.fit_step(consts, inp["params"], inp["center3d"], inp["cube"], target)
+
+    return step, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    step, cores = cpu_pipeline(batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    sample = (f"{args.steps} steps x {batch} hands (of the {args.batch}-hand workload), 128x128, oracle port: torch MANO "
+              f"restatement + C/OpenMP pytorch3d-0.4.0 naive rasteriser + m2d loss + autograd backward")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE.json configs[2]: large-batch render-loss fwd/bwd, {args.batch} hands per GPU, "
+                    f"128x128 depth, direct crop raster, NYU intrinsics, synthetic hand-shaped MANO (778v/1554f)",
+        "hands_per_gpu": args.batch, "global_batch": args.batch * world, "crop": CROP, "views": 1,
+        "parallelism": f"batch-sharded x{world}",
+        "l2_policy": "inputs larger than L2 (target+rendered images %.0f MB per step vs 126 MB L2)"
+                     % (2 * args.batch * CROP * CROP * 4 / 1e6),
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def time_region(fn, iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters     # ms
+
+
+def stage_times(step, iters=10):
+    """CUDA-event time of each stage of the step, launched alone through the C ABI (same stream)."""
+    import ctypes as C
+
+    from dsf_b200 import _lib as L
+
+    lib = L.lib()
+    B, R, h = step.B, step.R, step.layer._handle
+    s = L.stream_ptr()
+    ws = step.ws
+    g_img = torch.zeros(B, R, R, device=step.dev)
+    g_verts = torch.zeros(B, 779, 3, device=step.dev)
+    vcam = (step.verts * step.cube[:, None] / 2 + step.center3d[:, None]).contiguous()
+    prm = step.params
+    p = L.DsfManoParams(prm.data_ptr(), 62, 3, prm.data_ptr() + 12, 62, 45, prm.data_ptr() + 192, 62,
+                        prm.data_ptr() + 232, 62)
+    gp = step.g_params
+    g = L.DsfManoGrads(gp.data_ptr(), 62, gp.data_ptr() + 12, 62, gp.data_ptr() + 192, 62, gp.data_ptr() + 232, 62)
+    mws = torch.empty(lib.dsf_mano_workspace_floats(B), device=step.dev)
+    stages = {
+        "mano_forward(3 kernels)": lambda: L.check(lib.dsf_mano_forward(
+            h, B, C.byref(p), 8.0, step.verts.data_ptr(), step.joints.data_ptr(), None, mws.data_ptr(), s)),
+        "raster_fwd_kernel": lambda: L.check(lib.dsf_raster_forward(
+            h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
+            step.img.data_ptr(), step.p2f.data_ptr(), None, None, None, s)),
+        "depth_loss(2 kernels)": lambda: L.check(lib.dsf_depth_loss(
+            0, B, R, step.target.data_ptr(), step.img.data_ptr(), 0.99, 0.1, step.parts.data_ptr(),
+            step.totals.data_ptr(), g_img.data_ptr(), s)),
+        "raster_bwd_kernel": lambda: L.check(lib.dsf_raster_backward(
+            h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
+            step.p2f.data_ptr(), g_img.data_ptr(), g_verts.data_ptr(), s)),
+        "mano_backward(3 kernels)": lambda: L.check(lib.dsf_mano_backward(
+            h, B, C.byref(p), 8.0, step.verts.data_ptr(), step.joints.data_ptr(), g_verts.data_ptr(), None,
+            C.byref(g), mws.data_ptr(), s)),
+    }
+    out = {}
+    for name, fn in stages.items():
+        fn()
+        out[name] = time_region(fn, iters)
+    return out
+
+
+def run_ours(args):
+    from dsf_b200 import dist as D
+    from dsf_b200 import make_synthetic_mano, sample_fit_inputs
+    from dsf_b200.fit import FitStep
+    from dsf_b200.mano_layer import MANO_SMPL
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: dsf_b200 has no CPU fallback")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    layer = MANO_SMPL(make_synthetic_mano(0), "nyu")
+    inp = sample_fit_inputs(B, seed=1000 + rank)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
+    step = FitStep(layer, B, CROP, use_graph=not args.no_graph)
+    step.set_inputs(host["params"].to(dev), host["center3d"].to(dev), host["cube"].to(dev))
+    step.render_target(host["params_target"].to(dev))
+    torch.cuda.synchronize()
+    host_target = step.target.cpu().pin_memory()
+    packed = torch.zeros(D.PACK, device=dev)
+
+    def one_step():
+        step.step()
+        if world > 1:
+            # packed loss record: [sum_b per-hand loss * weight, sum |d|, mask count, n_hands]
+            packed[0] = step.totals[0] * B
+            packed[1:3] = step.totals[1:3]
+            packed[3] = float(B)
+            D.allreduce_totals(packed)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    with ClockSampler(local) as clk:
+        ms = time_region(one_step, args.steps)
+        if args.steps * ms < 1500:      # keep the sampler alive long enough to see clocks under load
+            time_region(one_step, int(1500 / max(ms, 1e-3)) + 1)
+    if world > 1:
+        torch.distributed.barrier()
+    ms = D.max_over_ranks(ms, dev)
+    value = B * world / (ms * 1e-3)
+    launches = step.launches_per_step * args.steps
+
+    # ---- end to end through the public call with host buffers: H2D inputs, step, D2H results ----
+    h_g = torch.empty(B, 62).pin_memory()
+    h_tot = torch.empty(4).pin_memory()
+
+    def e2e_step():
+        step.set_inputs(host["params"], host["center3d"], host["cube"], host_target)
+        step.step()
+        h_g.copy_(step.g_params, non_blocking=True)
+        h_tot.copy_(step.totals, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    e2e_iters = max(3, min(args.steps, 20))
+    if world > 1:
+        torch.distributed.barrier()
+    t_e2e = D.max_over_ranks(time_region(e2e_step, e2e_iters), dev)
+    h2d = B * (62 + 3 + 3 + CROP * CROP) * 4
+    d2h = B * 62 * 4 + 16
+    e2e = {"value": B * world / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world, "ms_per_step": t_e2e}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel, timed live with CUDA events ----
+    peak, peak_src = measured_peaks()
+    st = stage_times(step)
+    dom = max(st, key=st.get)
+    dom_ms = st["raster_fwd_kernel"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get("raster_fwd_kernel", {}).get(str(B))
+        except Exception:
+            traffic = None
+    achieved = RASTER_BYTES_PER_HAND * B / (dom_ms * 1e-3) / 1e9
+    step_gbs = BYTES_PER_FIT * B / (ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "raster_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_launch": RASTER_BYTES_PER_HAND * B, "kernel_ms": dom_ms,
+        "stage_ms": st, "slowest_stage": dom,
+        "step": {"bytes_per_fit": BYTES_PER_FIT, "achieved": step_gbs, "frac": step_gbs / peak},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cstep, cores = cpu_pipeline(args.ref_batch)
+        cstep()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < args.cpu_seconds:
+            cstep()
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": args.ref_batch * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} steps x {args.ref_batch} hands of the same workload (128x128, direct raster), "
+                         f"oracle port of the reference CPU path, {dt:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+        "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph,
+        "roofline": roofline, "cpu_baseline": cpu, "loss": float(step.totals[0]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=4096, help="hands per GPU")
+    ap.add_argument("--ref-batch", type=int, default=32, help="hands per CPU reference step (bounded sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

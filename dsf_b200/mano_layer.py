@@ -288,13 +288,13 @@ class MANO_SMPL(nn.Module):
         return m
 
     def __del__(self):
-        h = getattr(self, "_handle", None)
-        if h is not None and h.value:
-            try:
-                self._free(h)
-            except Exception:
-                pass
-            self._handle = None
+        try:
+            h = self.__dict__.get("_handle")
+            if h is not None and h.value:
+                self.__dict__["_handle"] = None
+                self.__dict__["_free"](h)
+        except Exception:
+            pass
 
     # -- M1 ------------------------------------------------------------------------------------------
     def _run(self, beta, theta, quat, cam, unit_scale):
