@@ -45,6 +45,7 @@ struct DsfMano {
     float* jr_w;
     int jr_nnz;
     int* faces;    // (n_faces,3)
+    unsigned int* faces_packed;   // (n_faces) i0 | i1 << 10 | i2 << 20
     int n_faces;
     float* coll_mask;  // (66,66)
     int parents[NJ];

@@ -130,6 +130,11 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     rc |= upload(&h->jr_idx, idx.data(), idx.size());
     rc |= upload(&h->jr_w, w.data(), w.size());
     rc |= upload(&h->faces, host->faces, (size_t)host->n_faces * 3);
+    std::vector<unsigned int> fpk(host->n_faces);
+    for (int f = 0; f < host->n_faces; ++f)
+        fpk[f] = (unsigned)host->faces[3 * f] | ((unsigned)host->faces[3 * f + 1] << 10) |
+                 ((unsigned)host->faces[3 * f + 2] << 20);
+    rc |= upload(&h->faces_packed, fpk.data(), fpk.size());
     rc |= upload(&h->coll_mask, mask.data(), mask.size());
     h->n_faces = host->n_faces;
     if (rc) {
@@ -143,7 +148,7 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
 extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
     void* ptrs[] = {h->Dmat, h->DmatT, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
-                    h->jr_ptr, h->jr_idx, h->jr_w, h->faces, h->coll_mask};
+                    h->jr_ptr, h->jr_idx, h->jr_w, h->faces, h->faces_packed, h->coll_mask};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free(h);

@@ -249,97 +249,249 @@ __device__ __forceinline__ float seg_dist_rn(float px, float py, float ax, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: grid (tiles, meshes); each CTA owns a TILE x TILE pixel block of one mesh
+// forward: grid (tiles, meshes); one CTA owns a 128 x 64 pixel tile of one mesh (half the image at
+// R = 128) with its z-buffer in shared memory as packed 64-bit (depth bits << 32 | face) keys.
+// Work is re-balanced twice through shared-memory lists so that lanes stay busy:
+//   phase A  thread per face   : cull, exact pixel bbox, emit one item per (row, <= 8 pixel segment)
+//   phase B  thread per item   : exact edge-sign pre-test of the segment's pixels, emit candidates
+//   phase C  thread per cand.  : full oracle-order fragment evaluation + atomicMin on the key
+// List overflow falls back to evaluating in place, so any mesh / crop size is handled.
 // ------------------------------------------------------------------------------------------------
-#define RT_TILE 64
-#define RT_THREADS 256
+#define RT_TW 128            // tile width  (pixels)
+#define RT_TH 64             // tile height: 64 KB of keys -> two CTAs per SM
+#define RT_THREADS 512
 #define RT_MAXR 512
+#define RT_CAP 4096          // entries per list
+#define RT_SEG 8
+#define RT_MAXF 2047         // face id is packed into 11 bits
 
-__global__ void __launch_bounds__(RT_THREADS)
+struct RasterSmem {
+    unsigned long long* key;   // RT_TW * RT_TH
+    float* vn;                 // NVW * 3 (x_ndc, y_ndc, z)
+    float* xs;                 // R
+    float* ys;                 // R
+    unsigned int* fp;          // F packed vertex ids
+    unsigned int* items;       // RT_CAP
+    unsigned int* cands;       // RT_CAP
+    int* counters;             // [0] items, [1] cands
+};
+
+__device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int F) {
+    RasterSmem s;
+    s.key = reinterpret_cast<unsigned long long*>(raw);
+    s.vn = reinterpret_cast<float*>(s.key + RT_TW * RT_TH);
+    s.xs = s.vn + 2340;
+    s.ys = s.xs + R;
+    s.fp = reinterpret_cast<unsigned int*>(s.ys + R);
+    s.items = s.fp + ((F + 3) & ~3);
+    s.cands = s.items + RT_CAP;
+    s.counters = reinterpret_cast<int*>(s.cands + RT_CAP);
+    return s;
+}
+
+static size_t raster_fwd_smem(int R, int F) {
+    return (size_t)RT_TW * RT_TH * 8 + 2340 * 4 + (size_t)2 * R * 4 + (size_t)((F + 3) & ~3) * 4 +
+           (size_t)2 * RT_CAP * 4 + 16;
+}
+
+// exact evaluation of pixel (i,j) against face f, commit to the z-buffer
+__device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned int f, int i, int j, int tx0,
+                                                int ty0) {
+    const unsigned int pk = s.fp[f];
+    const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+    const float z0 = s.vn[3 * a0 + 2], z1 = s.vn[3 * a1 + 2], z2 = s.vn[3 * a2 + 2];
+    unsigned long long* slot = &s.key[(j - ty0) * RT_TW + (i - tx0)];
+    // early z: pz is a convex combination of (z0,z1,z2) up to a few ulp, so a face whose nearest
+    // vertex is clearly behind the stored depth cannot win (NaN compare = empty pixel = proceed)
+    const float cur = __uint_as_float((unsigned int)(*slot >> 32));
+    if (fminf(z0, fminf(z1, z2)) * 0.99999f > cur) return;
+    const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
+    const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
+    const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
+    const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
+    FragEval fe = eval_fragment(s.xs[i], s.ys[j], x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
+    if (!fe.ok) return;
+    const float pz = fe.pz + 0.f;                               // -0 -> +0 so the bit pattern orders
+    atomicMin(slot, ((unsigned long long)__float_as_uint(pz) << 32) | f);
+}
+
+// pre-test of one row segment: bit k of the result = pixel i0+k passes the edge-sign test
+__device__ __forceinline__ unsigned int segment_hits(const RasterSmem& s, unsigned int f, int i0, int len, int j) {
+    const unsigned int pk = s.fp[f];
+    const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+    const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
+    const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
+    const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
+    const float py = s.ys[j];
+    // edge deltas: the same single roundings the oracle performs inline
+    const float d0y = __fsub_rn(y2, y1), d1y = __fsub_rn(y0, y2), d2y = __fsub_rn(y1, y0);
+    const float r0 = __fmul_rn(__fsub_rn(py, y1), __fsub_rn(x2, x1));
+    const float r1 = __fmul_rn(__fsub_rn(py, y2), __fsub_rn(x0, x2));
+    const float r2 = __fmul_rn(__fsub_rn(py, y0), __fsub_rn(x1, x0));
+    unsigned int hits = 0;
+#pragma unroll
+    for (int k = 0; k < RT_SEG; ++k) {
+        if (k < len) {
+            const float px = s.xs[i0 + k];
+            const float e0 = __fsub_rn(__fmul_rn(__fsub_rn(px, x1), d0y), r0);
+            const float e1 = __fsub_rn(__fmul_rn(__fsub_rn(px, x2), d1y), r1);
+            const float e2 = __fsub_rn(__fmul_rn(__fsub_rn(px, x0), d2y), r2);
+            // all three barycentrics share the sign of e_i / area; mixed signs can never be inside
+            const bool pos = e0 > 0.f && e1 > 0.f && e2 > 0.f;
+            const bool neg = e0 < 0.f && e1 < 0.f && e2 < 0.f;
+            if (pos || neg) hits |= 1u << k;
+        }
+    }
+    return hits;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 2)
 raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const float* __restrict__ place_scale,
-                  const float* __restrict__ place_off, const int* __restrict__ faces, int F,
+                  const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed, int F,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);
-    float* svn = reinterpret_cast<float*>(skey + RT_TILE * RT_TILE);
-    float* sxs = svn + NVW * 3;
-    float* sys = sxs + R;
+    const RasterSmem s = carve_smem(smem_raw, R, F);
     const int mesh = blockIdx.y;
     const int tile = blockIdx.x;
-    const int tx0 = (tile % tiles_x) * RT_TILE, ty0 = (tile / tiles_x) * RT_TILE;
-    const int tx1 = min(R, tx0 + RT_TILE) - 1, ty1 = min(R, ty0 + RT_TILE) - 1;
-    const int tid = threadIdx.x;
+    const int tx0 = (tile % tiles_x) * RT_TW, ty0 = (tile / tiles_x) * RT_TH;
+    const int tx1 = min(R, tx0 + RT_TW) - 1, ty1 = min(R, ty0 + RT_TH) - 1;
+    const int tid = threadIdx.x, lane = tid & 31;
     const ViewRec vw = load_view(view + (size_t)mesh * VIEW);
 
     for (int i = tid; i < R; i += RT_THREADS) {
-        sxs[i] = xs_g[(size_t)mesh * R + i];
-        sys[i] = ys_g[(size_t)mesh * R + i];
+        s.xs[i] = xs_g[(size_t)mesh * R + i];
+        s.ys[i] = ys_g[(size_t)mesh * R + i];
     }
+    for (int i = tid; i < F; i += RT_THREADS) s.fp[i] = faces_packed[i];
     const float* vm = verts + (size_t)mesh * NVW * 3;
     const float* ps = place_scale ? place_scale + 3 * mesh : nullptr;
     const float* po = place_off ? place_off + 3 * mesh : nullptr;
-    for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(vm + 3 * v, ps, po, vw, svn + 3 * v);
-    for (int i = tid; i < RT_TILE * RT_TILE; i += RT_THREADS) skey[i] = ~0ull;
+    for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(vm + 3 * v, ps, po, vw, s.vn + 3 * v);
+    {
+        ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s.key);
+        for (int i = tid; i < RT_TW * RT_TH / 2; i += RT_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
+    }
+    if (tid < 2) s.counters[tid] = 0;
     __syncthreads();
 
     const int cx0 = max(tx0, vw.xlo), cx1 = min(tx1, vw.xhi);
     const int cy0 = max(ty0, vw.ylo), cy1 = min(ty1, vw.yhi);
-    if (cx0 <= cx1 && cy0 <= cy1) {
-        for (int f = tid; f < F; f += RT_THREADS) {
-            const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-            const float x0 = svn[3 * i0], y0 = svn[3 * i0 + 1], z0 = svn[3 * i0 + 2];
-            const float x1 = svn[3 * i1], y1 = svn[3 * i1 + 1], z1 = svn[3 * i1 + 2];
-            const float x2 = svn[3 * i2], y2 = svn[3 * i2 + 1], z2 = svn[3 * i2 + 2];
-            const float zmin = fminf(z0, fminf(z1, z2));
-            if (!(zmin >= EPS)) continue;                       // behind / at the camera
-            const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
-            const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
-            const int ia = max(cx0, first_le(sxs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
-            const int ib = min(cx1, last_ge(sxs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
-            if (ia > ib) continue;
-            const int ja = max(cy0, first_le(sys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
-            const int jb = min(cy1, last_ge(sys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
-            if (ja > jb) continue;
-            const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
-            if (farea <= EPS && farea >= -EPS) continue;        // degenerate in NDC
-            const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
-            // per-face edge deltas (same single roundings the oracle performs inline)
-            const float d0y = __fsub_rn(y2, y1), d0x = __fsub_rn(x2, x1);
-            const float d1y = __fsub_rn(y0, y2), d1x = __fsub_rn(x0, x2);
-            const float d2y = __fsub_rn(y1, y0), d2x = __fsub_rn(x1, x0);
-            for (int j = ja; j <= jb; ++j) {
-                const float py = sys[j];
-                const float r0 = __fmul_rn(__fsub_rn(py, y1), d0x);
-                const float r1 = __fmul_rn(__fsub_rn(py, y2), d1x);
-                const float r2 = __fmul_rn(__fsub_rn(py, y0), d2x);
-                for (int i = ia; i <= ib; ++i) {
-                    const float px = sxs[i];
-                    const float e0 = __fsub_rn(__fmul_rn(__fsub_rn(px, x1), d0y), r0);
-                    const float e1 = __fsub_rn(__fmul_rn(__fsub_rn(px, x2), d1y), r1);
-                    const float e2 = __fsub_rn(__fmul_rn(__fsub_rn(px, x0), d2y), r2);
-                    const bool pos = e0 > 0.f && e1 > 0.f && e2 > 0.f;
-                    const bool neg = e0 < 0.f && e1 < 0.f && e2 < 0.f;
-                    if (!(pos || neg)) continue;                // some w_i <= 0: cannot be inside
-                    FragEval fe = eval_fragment(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
-                    if (!fe.ok) continue;
-                    const float pz = fe.pz + 0.f;               // -0 -> +0 so the bit pattern orders
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned int)f;
-                    atomicMin(&skey[(j - ty0) * RT_TILE + (i - tx0)], key);
+    const bool tile_live = cx0 <= cx1 && cy0 <= cy1;
+    const int n_rounds = (F + 2 * RT_THREADS - 1) / (2 * RT_THREADS);
+    const int chunk = (F + n_rounds - 1) / n_rounds;
+    for (int round = 0; round < n_rounds && tile_live; ++round) {
+        const int f_lo = round * chunk, f_hi = min(F, f_lo + chunk);
+        // ---------------- phase A: faces -> row-segment items ----------------
+        for (int fb = f_lo + (tid & ~31); fb < f_hi; fb += RT_THREADS) {
+            const int f = fb + lane;
+            int ia = 0, ib = -1, ja = 0, jb = -1;
+            if (f < f_hi) {
+                const unsigned int pk = s.fp[f];
+                const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+                const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1], z0 = s.vn[3 * a0 + 2];
+                const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1], z1 = s.vn[3 * a1 + 2];
+                const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
+                const float zmin = fminf(z0, fminf(z1, z2));
+                const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
+                // behind / at the camera, or degenerate in NDC
+                if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
+                    const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
+                    const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
+                    ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
+                    ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
+                    if (ia <= ib) {
+                        ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
+                        jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
+                    }
+                }
+            }
+            const int w = ib - ia + 1, hgt = jb - ja + 1;
+            const int nseg = (w + RT_SEG - 1) / RT_SEG;
+            const int n = (w > 0 && hgt > 0) ? nseg * hgt : 0;
+            int total;
+            const int excl = warp_excl_scan(n, lane, &total);
+            int base = 0;
+            if (lane == 0 && total > 0) base = atomicAdd(&s.counters[0], total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int slot = base + excl;
+            for (int j = ja; j <= jb && n > 0; ++j) {
+                for (int i0 = ia; i0 <= ib; i0 += RT_SEG, ++slot) {
+                    const int len = min(RT_SEG, ib - i0 + 1);
+                    if (slot < RT_CAP) {
+                        s.items[slot] = (unsigned int)f | ((unsigned int)(j - ty0) << 11) |
+                                        ((unsigned int)(i0 - tx0) << 18) | ((unsigned int)(len - 1) << 25);
+                    } else {                                     // list full: evaluate in place
+                        unsigned int hits = segment_hits(s, f, i0, len, j);
+                        while (hits) {
+                            const int k = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            eval_and_commit(s, f, i0 + k, j, tx0, ty0);
+                        }
+                    }
                 }
             }
         }
+        __syncthreads();
+        // ---------------- phase B: items -> candidates ----------------
+        const int n_items = min(s.counters[0], RT_CAP);
+        for (int ib0 = tid & ~31; ib0 < n_items; ib0 += RT_THREADS) {
+            const int it = ib0 + lane;
+            unsigned int hits = 0, f = 0;
+            int i0 = 0, j = 0;
+            if (it < n_items) {
+                const unsigned int e = s.items[it];
+                f = e & 2047u;
+                j = ty0 + (int)((e >> 11) & 127u);
+                i0 = tx0 + (int)((e >> 18) & 127u);
+                hits = segment_hits(s, f, i0, (int)((e >> 25) & 7u) + 1, j);
+            }
+            int total;
+            const int excl = warp_excl_scan(__popc(hits), lane, &total);
+            int base = 0;
+            if (lane == 0 && total > 0) base = atomicAdd(&s.counters[1], total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int slot = base + excl;
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                if (slot < RT_CAP)
+                    s.cands[slot] = f | ((unsigned int)(j - ty0) << 11) | ((unsigned int)(i0 + k - tx0) << 18);
+                else
+                    eval_and_commit(s, f, i0 + k, j, tx0, ty0);
+                ++slot;
+            }
+        }
+        __syncthreads();
+        // ---------------- phase C: candidates -> z-buffer ----------------
+        const int n_cands = min(s.counters[1], RT_CAP);
+        for (int c = tid; c < n_cands; c += RT_THREADS) {
+            const unsigned int e = s.cands[c];
+            eval_and_commit(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0);
+        }
+        __syncthreads();
+        if (tid < 2) s.counters[tid] = 0;
+        __syncthreads();
     }
-    __syncthreads();
 
     // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299)
     const float zmax = __fadd_rn(vw.zc, vw.zh), zmin_c = __fsub_rn(vw.zc, vw.zh);
     const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
     for (int k = tid; k < tw * th; k += RT_THREADS) {
         const int lx = k % tw, ly = k / tw;
-        const unsigned long long key = skey[ly * RT_TILE + lx];
+        const unsigned long long key = s.key[ly * RT_TW + lx];
         const int f = key == ~0ull ? -1 : (int)(unsigned int)(key & 0xffffffffu);
         const float z = f < 0 ? -1.f : __uint_as_float((unsigned int)(key >> 32));
         float d = z <= 0.f ? 0.f : z;
@@ -353,11 +505,12 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         if (bary || dists) {
             float b0 = -1.f, b1 = -1.f, b2 = -1.f, dd = -1.f;
             if (f >= 0) {
-                const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-                const float x0 = svn[3 * i0], y0 = svn[3 * i0 + 1], z0 = svn[3 * i0 + 2];
-                const float x1 = svn[3 * i1], y1 = svn[3 * i1 + 1], z1 = svn[3 * i1 + 2];
-                const float x2 = svn[3 * i2], y2 = svn[3 * i2 + 1], z2 = svn[3 * i2 + 2];
-                const float px = sxs[tx0 + lx], py = sys[ty0 + ly];
+                const unsigned int pk = s.fp[f];
+                const int i0 = pk & 1023, i1 = (pk >> 10) & 1023, i2 = pk >> 20;
+                const float x0 = s.vn[3 * i0], y0 = s.vn[3 * i0 + 1], z0 = s.vn[3 * i0 + 2];
+                const float x1 = s.vn[3 * i1], y1 = s.vn[3 * i1 + 1], z1 = s.vn[3 * i1 + 2];
+                const float x2 = s.vn[3 * i2], y2 = s.vn[3 * i2 + 1], z2 = s.vn[3 * i2 + 2];
+                const float px = s.xs[tx0 + lx], py = s.ys[ty0 + ly];
                 const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
                 FragEval fe = eval_fragment(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
                 b0 = fe.b0; b1 = fe.b1; b2 = fe.b2;
@@ -374,27 +527,28 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     }
 }
 
-static size_t raster_fwd_smem(int R) {
-    return (size_t)RT_TILE * RT_TILE * 8 + (size_t)NVW * 3 * 4 + (size_t)2 * R * 4;
-}
-
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
                             cudaStream_t st) {
-    const int tiles_x = (R + RT_TILE - 1) / RT_TILE;
-    const size_t smem = raster_fwd_smem(R);
+    if (h->n_faces > RT_MAXF) {
+        dsf_set_error("rasteriser supports at most %d faces (got %d)", RT_MAXF, h->n_faces);
+        return DSF_ERR_UNSUPPORTED;
+    }
+    const int tiles_x = (R + RT_TW - 1) / RT_TW, tiles_y = (R + RT_TH - 1) / RT_TH;
+    const size_t smem = raster_fwd_smem(R, h->n_faces);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 16 || !attr_set[dev]) {
         DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)raster_fwd_smem(RT_MAXR)));
+                                            (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
         if (dev < 16) attr_set[dev] = true;
     }
-    dim3 grid(tiles_x * tiles_x, n_mesh);
-    raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off, h->faces,
-                                                      h->n_faces, view, xs, ys, img, p2f, zbuf, bary, dists);
+    dim3 grid(tiles_x * tiles_y, n_mesh);
+    raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
+                                                      h->faces_packed, h->n_faces, view, xs, ys, img, p2f,
+                                                      zbuf, bary, dists);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -445,16 +599,40 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     const float inv_zh = 1.f / vw.zh;
     const int* pf = p2f + (size_t)mesh * R * R;
     const float* gi = g_img + (size_t)mesh * R * R;
-    for (int k = tid; k < R * R; k += RB_THREADS) {
-        const int f = pf[k];
-        if (f < 0) continue;
-        const float g = gi[k];
-        if (g == 0.f) continue;
+    // Only ~20 % of the pixels are foreground: each warp compacts the live pixels of successive
+    // 32-pixel chunks into a private queue and runs the (long) gradient body on full warps.
+    __shared__ int s_queue[RB_THREADS / 32][64];
+    const int warp = tid >> 5, lane = tid & 31;
+    int* q = s_queue[warp];
+    int queued = 0;
+    const int n_pix = R * R;
+    for (int base = warp * 32; base < n_pix || queued > 0; base += RB_THREADS) {
+        if (base < n_pix) {
+            const int k = base + lane;
+            const bool live = k < n_pix && pf[k] >= 0 && gi[k] != 0.f;
+            const unsigned int m = __ballot_sync(0xffffffffu, live);
+            if (live) q[queued + __popc(m & ((1u << lane) - 1u))] = k;
+            queued += __popc(m);
+            __syncwarp();
+            if (queued < 32 && base + RB_THREADS < n_pix) continue;
+        }
+        const int take = min(queued, 32);
+        const int k = lane < take ? q[lane] : -1;
+        const int carry = (lane + 32 < queued) ? q[lane + 32] : 0;
+        __syncwarp();
+        if (lane + 32 < queued) q[lane] = carry;
+        queued -= take;
+        __syncwarp();
+        // every lane stays in the body (inactive ones carry zeros) so the warp can reduce per face
+        bool act = k >= 0;
+        const int kk = act ? k : 0;
+        const int f = act ? pf[kk] : 0;
+        const float g = act ? gi[kk] : 0.f;
         const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
         const float x0 = svn[3 * i0], y0 = svn[3 * i0 + 1], z0 = svn[3 * i0 + 2];
         const float x1 = svn[3 * i1], y1 = svn[3 * i1 + 1], z1 = svn[3 * i1 + 2];
         const float x2 = svn[3 * i2], y2 = svn[3 * i2 + 1], z2 = svn[3 * i2 + 2];
-        const float px = sxs[k % R], py = sys[k / R];
+        const float px = sxs[kk % R], py = sys[kk / R];
         const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
         const float e0 = edge_rn(px, py, x1, y1, x2, y2);
         const float e1 = edge_rn(px, py, x2, y2, x0, y0);
@@ -467,26 +645,46 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
         const float b0 = t0 * id, b1 = t1 * id, b2 = t2 * id;
         const float pz = b0 * z0 + b1 * z1 + b2 * z2;
         // gates of the forward epilogue: background fill and the [zmin,zmax] clamp pass no gradient
-        if (!(pz > 0.f) || pz > zmax || pz < zmin_c) continue;
-        const float gz = g * inv_zh;
+        act = act && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
+        const float gz = act ? g * inv_zh : 0.f;
         const float gb0 = gz * z0, gb1 = gz * z1, gb2 = gz * z2;
-        const float s = (gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
-        const float gt0 = gb0 * id - s, gt1 = gb1 * id - s, gt2 = gb2 * id - s;
+        const float sgb = (gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
+        const float gt0 = gb0 * id - sgb, gt1 = gb1 * id - sgb, gt2 = gb2 * id - sgb;
         const float gw0 = gt0 * z1 * z2, gw1 = gt1 * z0 * z2, gw2 = gt2 * z0 * z1;
-        const float gz0 = gz * b0 + gt1 * w1 * z2 + gt2 * z1 * w2;
-        const float gz1 = gz * b1 + gt0 * w0 * z2 + gt2 * z0 * w2;
-        const float gz2 = gz * b2 + gt0 * w0 * z1 + gt1 * z0 * w1;
         const float ge0 = gw0 * ia, ge1 = gw1 * ia, ge2 = gw2 * ia;
         const float garea = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * ia * ia;
-        float gx0 = ge1 * (y2 - py) + ge2 * (py - y1) + garea * (y2 - y1);
-        float gy0 = ge1 * (px - x2) + ge2 * (x1 - px) + garea * (x1 - x2);
-        float gx1 = ge0 * (py - y2) + ge2 * (y0 - py) + garea * (y0 - y2);
-        float gy1 = ge0 * (x2 - px) + ge2 * (px - x0) + garea * (x2 - x0);
-        float gx2 = ge0 * (y1 - py) + ge1 * (py - y0) + garea * (y1 - y0);
-        float gy2 = ge0 * (px - x1) + ge1 * (x0 - px) - garea * (x1 - x0);
-        atomicAdd(&sgn[3 * i0], gx0); atomicAdd(&sgn[3 * i0 + 1], gy0); atomicAdd(&sgn[3 * i0 + 2], gz0);
-        atomicAdd(&sgn[3 * i1], gx1); atomicAdd(&sgn[3 * i1 + 1], gy1); atomicAdd(&sgn[3 * i1 + 2], gz1);
-        atomicAdd(&sgn[3 * i2], gx2); atomicAdd(&sgn[3 * i2 + 1], gy2); atomicAdd(&sgn[3 * i2 + 2], gz2);
+        float gv[9];
+        gv[0] = ge1 * (y2 - py) + ge2 * (py - y1) + garea * (y2 - y1);
+        gv[1] = ge1 * (px - x2) + ge2 * (x1 - px) + garea * (x1 - x2);
+        gv[2] = gz * b0 + gt1 * w1 * z2 + gt2 * z1 * w2;
+        gv[3] = ge0 * (py - y2) + ge2 * (y0 - py) + garea * (y0 - y2);
+        gv[4] = ge0 * (x2 - px) + ge2 * (px - x0) + garea * (x2 - x0);
+        gv[5] = gz * b1 + gt0 * w0 * z2 + gt2 * z0 * w2;
+        gv[6] = ge0 * (y1 - py) + ge1 * (py - y0) + garea * (y1 - y0);
+        gv[7] = ge0 * (px - x1) + ge1 * (x0 - px) - garea * (x1 - x0);
+        gv[8] = gz * b2 + gt0 * w0 * z1 + gt1 * z0 * w1;
+        // Neighbouring pixels mostly hit the same face, and float atomics on shared memory are CAS
+        // loops that serialise on equal addresses: sum each run of equal face ids inside the warp
+        // (segmented scan) and let only the last lane of a run touch shared memory.
+        const int key = act ? f : -1 - lane;
+        const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || key != key_prev;
+        const unsigned int heads = __ballot_sync(0xffffffffu, head);
+        const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const float t = __shfl_up_sync(0xffffffffu, gv[e], o);
+                if (lane - o >= run_start) gv[e] += t;
+            }
+        }
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (act && tail) {
+            atomicAdd(&sgn[3 * i0], gv[0]); atomicAdd(&sgn[3 * i0 + 1], gv[1]); atomicAdd(&sgn[3 * i0 + 2], gv[2]);
+            atomicAdd(&sgn[3 * i1], gv[3]); atomicAdd(&sgn[3 * i1 + 1], gv[4]); atomicAdd(&sgn[3 * i1 + 2], gv[5]);
+            atomicAdd(&sgn[3 * i2], gv[6]); atomicAdd(&sgn[3 * i2 + 1], gv[7]); atomicAdd(&sgn[3 * i2 + 2], gv[8]);
+        }
     }
     __syncthreads();
     float* go = g_verts + (size_t)mesh * NVW * 3;
