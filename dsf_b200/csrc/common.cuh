@@ -44,6 +44,9 @@ struct DsfMano {
     int* jr_idx;
     float* jr_w;
     int jr_nnz;
+    int* wj_ptr;   // (17) CSR of the skin weights, joint-major
+    int* wj_idx;
+    float* wj_w;
     int* faces;    // (n_faces,3)
     unsigned int* faces_packed;   // (n_faces) i0 | i1 << 10 | i2 << 20
     int n_faces;

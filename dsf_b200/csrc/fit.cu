@@ -9,18 +9,20 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
 int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale,
                            const float* verts, const float* joints, const float* g_verts,
                            const float* g_joints, const DsfManoGrads* g, float* ws, cudaStream_t st);
+int dsf_raster_tiles(int R);
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
-                            cudaStream_t st);
+                            const float* target, float thr, float* parts_tile, cudaStream_t st);
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
-                             int R, const int* p2f, const float* g_img, float* g_verts, cudaStream_t st);
-int dsf_depth_loss_impl(int mode, int B, int R, const float* real, const float* synth, float thr, float weight,
-                        float* parts, float* totals, float* g_synth, cudaStream_t st);
+                             int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
+                             const float* img, const float* parts, float gscale, float thr, cudaStream_t st);
+int dsf_fold_loss_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
+                       cudaStream_t st);
 
 extern "C" long dsf_fit_workspace_floats(int batch, int R) {
-    return (long)batch * (WS_PER_HAND + (long)R * R + NVW * 3);
+    return (long)batch * (WS_PER_HAND + 2L * dsf_raster_tiles(R) + NVW * 3);
 }
 
 extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
@@ -35,8 +37,10 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws_mano = workspace;
-    float* g_img = workspace + (size_t)batch * WS_PER_HAND;
-    float* g_verts = g_img + (size_t)batch * R * R;
+    const int n_tiles = dsf_raster_tiles(R);
+    float* parts_tile = workspace + (size_t)batch * WS_PER_HAND;
+    float* g_verts = parts_tile + (size_t)batch * n_tiles * 2;
+    const float thr = 0.99f;
 
     // params (B,62) = [quat3 | theta45 | beta10 | scale, trans3]   (mano_layer.py:1073-1076)
     DsfManoParams p;
@@ -53,12 +57,15 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
 
     int rc = dsf_mano_forward_impl(h, batch, &p, unit_scale, verts, joints, nullptr, ws_mano, st);
     if (rc) return rc;
+    // rasterise + normalise; the m2d loss partial sums fall out of the epilogue (no extra pass)
     rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr,
-                                 nullptr, nullptr, st);
+                                 nullptr, nullptr, target, thr, parts_tile, st);
     if (rc) return rc;
-    rc = dsf_depth_loss_impl(0, batch, R, target, img, 0.99f, loss_weight, parts, totals, g_img, st);
+    rc = dsf_fold_loss_impl(batch, n_tiles, loss_weight, parts_tile, parts, totals, st);
     if (rc) return rc;
-    rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, g_img, g_verts, st);
+    // backward recomputes d loss / d img per pixel from (target, img, N_b): no gradient image in HBM
+    rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, nullptr,
+                                  g_verts, target, img, parts, loss_weight / (float)batch, thr, st);
     if (rc) return rc;
     rc = dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
     return rc;

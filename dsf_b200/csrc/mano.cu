@@ -114,6 +114,20 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     }
     h->jr_nnz = (int)idx.size();
     if (idx.empty()) { idx.push_back(0); w.push_back(0.f); }
+    // CSR of the skin weights (joint-major) for the g_A reduction of the backward pass
+    std::vector<int> wptr(NJ + 1, 0), widx;
+    std::vector<float> wval;
+    for (int j = 0; j < NJ; ++j) {
+        for (int v = 0; v < NV; ++v) {
+            float x = host->weights[v * NJ + j];
+            if (x != 0.f) {
+                widx.push_back(v);
+                wval.push_back(x);
+            }
+        }
+        wptr[j + 1] = (int)widx.size();
+    }
+    if (widx.empty()) { widx.push_back(0); wval.push_back(0.f); }
     std::vector<float> mask(DSF_NSPHERE * DSF_NSPHERE);
     dsf_build_collision_mask(mask.data());
 
@@ -129,6 +143,9 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     rc |= upload(&h->jr_ptr, ptr.data(), ptr.size());
     rc |= upload(&h->jr_idx, idx.data(), idx.size());
     rc |= upload(&h->jr_w, w.data(), w.size());
+    rc |= upload(&h->wj_ptr, wptr.data(), wptr.size());
+    rc |= upload(&h->wj_idx, widx.data(), widx.size());
+    rc |= upload(&h->wj_w, wval.data(), wval.size());
     rc |= upload(&h->faces, host->faces, (size_t)host->n_faces * 3);
     std::vector<unsigned int> fpk(host->n_faces);
     for (int f = 0; f < host->n_faces; ++f)
@@ -148,7 +165,8 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
 extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
     void* ptrs[] = {h->Dmat, h->DmatT, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
-                    h->jr_ptr, h->jr_idx, h->jr_w, h->faces, h->faces_packed, h->coll_mask};
+                    h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx, h->wj_w, h->faces, h->faces_packed,
+                    h->coll_mask};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free(h);
@@ -452,16 +470,18 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ 
 //   cotangents of verts/joints -> g_vposed (ws), g_A (ws), g_cam.
 // ------------------------------------------------------------------------------------------------
 #define SKB_T 128
-#define SKB_VPT ((NV + SKB_T - 1) / SKB_T)   // 7 vertices per thread
 
 __global__ void __launch_bounds__(SKB_T)
 mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
                      const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
-                     const float* __restrict__ jr_w, const float* __restrict__ cam, int ld_cam,
+                     const float* __restrict__ jr_w, const int* __restrict__ wj_ptr,
+                     const int* __restrict__ wj_idx, const float* __restrict__ wj_w,
+                     const float* __restrict__ cam, int ld_cam,
                      float unit_scale, const float* __restrict__ verts, const float* __restrict__ joints,
                      const float* __restrict__ g_verts, const float* __restrict__ g_joints,
                      float* __restrict__ g_cam, int ld_gcam) {
     __shared__ float sg[NVW * 3];
+    __shared__ float svp[NV * 3];
     __shared__ float sGr[NJ][9];
     __shared__ float sgj[NJOUT * 3];
     __shared__ float red[SKB_T / 32][12];
@@ -522,71 +542,60 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
         }
     }
     __syncthreads();
-    // per-vertex: g_vposed = T^T g ; keep (g, vp) in registers for the g_A reduction
-    float rg[SKB_VPT][3], rv[SKB_VPT][3];
+    // per-vertex: g_vposed = T^T g ; sg becomes the gradient wrt the unscaled skinned vertex
     const float* VP = wsh + WS_VP;
     float* GVP = wsh + WS_GVP;
+    for (int v = tid; v < NV; v += SKB_T) {
+        const float g0 = sg[3 * v] * s_tot, g1 = sg[3 * v + 1] * s_tot, g2 = sg[3 * v + 2] * s_tot;
+        sg[3 * v] = g0; sg[3 * v + 1] = g1; sg[3 * v + 2] = g2;
+        svp[3 * v] = VP[3 * v]; svp[3 * v + 1] = VP[3 * v + 1]; svp[3 * v + 2] = VP[3 * v + 2];
+        float T[9];
 #pragma unroll
-    for (int i = 0; i < SKB_VPT; ++i) {
-        int v = tid + i * SKB_T;
-        if (v < NV) {
-            float g0 = sg[3 * v] * s_tot, g1 = sg[3 * v + 1] * s_tot, g2 = sg[3 * v + 2] * s_tot;
-            rg[i][0] = g0; rg[i][1] = g1; rg[i][2] = g2;
-            rv[i][0] = VP[3 * v]; rv[i][1] = VP[3 * v + 1]; rv[i][2] = VP[3 * v + 2];
-            float T[9];
+        for (int e = 0; e < 9; ++e) T[e] = 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(W + v * NJ);
 #pragma unroll
-            for (int e = 0; e < 9; ++e) T[e] = 0.f;
-            for (int j = 0; j < NJ; ++j) {
-                float w = __ldg(W + v * NJ + j);
-                if (w != 0.f) {
+        for (int q = 0; q < 4; ++q) {
+            const float4 w4 = __ldg(wp + q);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int e = 0; e < 9; ++e) T[e] = fmaf(w, sGr[j][e], T[e]);
+            for (int i = 0; i < 4; ++i) {
+                if (wv[i] != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) T[e] = fmaf(wv[i], sGr[q * 4 + i][e], T[e]);
                 }
             }
-            GVP[3 * v] = T[0] * g0 + T[3] * g1 + T[6] * g2;
-            GVP[3 * v + 1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
-            GVP[3 * v + 2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
-        } else {
-            rg[i][0] = rg[i][1] = rg[i][2] = 0.f;
-            rv[i][0] = rv[i][1] = rv[i][2] = 0.f;
         }
+        GVP[3 * v] = T[0] * g0 + T[3] * g1 + T[6] * g2;
+        GVP[3 * v + 1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
+        GVP[3 * v + 2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
     }
     if (tid < NP - NV * 3) GVP[NV * 3 + tid] = 0.f;
-    // g_A[j] = sum_v w_vj [ g (x) vp | g ]
+    __syncthreads();
+    // g_A[j] = sum_v w_vj [ g (x) vp | g ] over the vertices joint j actually moves: one warp per
+    // joint walks that joint's weight list (CSR) and reduces with shuffles
     float* GA = wsh + WS_GA;
-    for (int j = 0; j < NJ; ++j) {
+    for (int j = warp; j < NJ; j += SKB_T / 32) {
         float acc[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+        for (int e = wj_ptr[j] + lane; e < wj_ptr[j + 1]; e += 32) {
+            const int v = wj_idx[e];
+            const float w = wj_w[e];
 #pragma unroll
-        for (int i = 0; i < SKB_VPT; ++i) {
-            int v = tid + i * SKB_T;
-            float w = (v < NV) ? __ldg(W + v * NJ + j) : 0.f;
-            if (w != 0.f) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    float wg = w * rg[i][r];
-                    acc[3 * r] = fmaf(wg, rv[i][0], acc[3 * r]);
-                    acc[3 * r + 1] = fmaf(wg, rv[i][1], acc[3 * r + 1]);
-                    acc[3 * r + 2] = fmaf(wg, rv[i][2], acc[3 * r + 2]);
-                    acc[9 + r] += wg;
-                }
+            for (int r = 0; r < 3; ++r) {
+                const float wg = w * sg[3 * v + r];
+                acc[3 * r] = fmaf(wg, svp[3 * v], acc[3 * r]);
+                acc[3 * r + 1] = fmaf(wg, svp[3 * v + 1], acc[3 * r + 1]);
+                acc[3 * r + 2] = fmaf(wg, svp[3 * v + 2], acc[3 * r + 2]);
+                acc[9 + r] += wg;
             }
         }
 #pragma unroll
         for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
         if (lane == 0) {
 #pragma unroll
-            for (int e = 0; e < 12; ++e) red[warp][e] = acc[e];
+            for (int e = 0; e < 12; ++e) GA[j * 12 + e] = acc[e];
         }
-        __syncthreads();
-        if (tid < 12) {
-            float a = 0.f;
-#pragma unroll
-            for (int w = 0; w < SKB_T / 32; ++w) a += red[w][tid];
-            GA[j * 12 + tid] = a;
-        }
-        __syncthreads();
     }
     // camera gradient
     if (g_cam) {
@@ -757,7 +766,8 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
     int rc = ensure_constants();
     if (rc) return rc;
     ChainTopo topo = topo_of(h);
-    mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
+    mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx,
+                                              h->wj_w, p->cam, p->ld_cam,
                                               unit_scale, verts, joints, g_verts, g_joints,
                                               p->cam ? g->cam : nullptr, g->ld_cam);
     DSF_CHECK_LAUNCH();

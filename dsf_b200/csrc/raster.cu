@@ -361,7 +361,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed, int F,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
-                  float* __restrict__ bary, float* __restrict__ dists) {
+                  float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
+                  float thr, float* __restrict__ parts_tile) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RasterSmem s = carve_smem(smem_raw, R, F);
     const int mesh = blockIdx.y;
@@ -486,51 +487,77 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         __syncthreads();
     }
 
-    // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299)
+    // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299); with a target image the
+    // m2d loss partial sums of this tile (train_render.py:728-731) are produced on the way out
     const float zmax = __fadd_rn(vw.zc, vw.zh), zmin_c = __fsub_rn(vw.zc, vw.zh);
     const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
-    for (int k = tid; k < tw * th; k += RT_THREADS) {
-        const int lx = k % tw, ly = k / tw;
-        const unsigned long long key = s.key[ly * RT_TW + lx];
-        const int f = key == ~0ull ? -1 : (int)(unsigned int)(key & 0xffffffffu);
-        const float z = f < 0 ? -1.f : __uint_as_float((unsigned int)(key >> 32));
-        float d = z <= 0.f ? 0.f : z;
-        d = (d == 0.f) ? zmax : d;
-        d = d > zmax ? zmax : d;
-        d = d < zmin_c ? zmin_c : d;
-        const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
-        img[o] = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
-        p2f[o] = f;
-        if (zbuf) zbuf[o] = z;
-        if (bary || dists) {
-            float b0 = -1.f, b1 = -1.f, b2 = -1.f, dd = -1.f;
-            if (f >= 0) {
-                const unsigned int pk = s.fp[f];
-                const int i0 = pk & 1023, i1 = (pk >> 10) & 1023, i2 = pk >> 20;
-                const float x0 = s.vn[3 * i0], y0 = s.vn[3 * i0 + 1], z0 = s.vn[3 * i0 + 2];
-                const float x1 = s.vn[3 * i1], y1 = s.vn[3 * i1 + 1], z1 = s.vn[3 * i1 + 2];
-                const float x2 = s.vn[3 * i2], y2 = s.vn[3 * i2 + 1], z2 = s.vn[3 * i2 + 2];
-                const float px = s.xs[tx0 + lx], py = s.ys[ty0 + ly];
-                const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
-                FragEval fe = eval_fragment(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
-                b0 = fe.b0; b1 = fe.b1; b2 = fe.b2;
-                float d01 = seg_dist_rn(px, py, x0, y0, x1, y1);
-                float d02 = seg_dist_rn(px, py, x0, y0, x2, y2);
-                float d12 = seg_dist_rn(px, py, x1, y1, x2, y2);
-                float m = d01 < d02 ? d01 : d02;
-                m = m < d12 ? m : d12;
-                dd = -m;
+    float l_sum = 0.f, l_cnt = 0.f;
+    for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
+        for (int lx = lane; lx < tw; lx += 32) {
+            const unsigned long long key = s.key[ly * RT_TW + lx];
+            const int f = key == ~0ull ? -1 : (int)(unsigned int)(key & 0xffffffffu);
+            const float z = f < 0 ? -1.f : __uint_as_float((unsigned int)(key >> 32));
+            float d = z <= 0.f ? 0.f : z;
+            d = (d == 0.f) ? zmax : d;
+            d = d > zmax ? zmax : d;
+            d = d < zmin_c ? zmin_c : d;
+            const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
+            const float val = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
+            img[o] = val;
+            p2f[o] = f;
+            if (target) {
+                const float t = target[o];
+                if (t < thr || val < thr) { l_sum += fabsf(t - val); l_cnt += 1.f; }
             }
-            if (bary) { bary[3 * o] = b0; bary[3 * o + 1] = b1; bary[3 * o + 2] = b2; }
-            if (dists) dists[o] = dd;
+            if (zbuf) zbuf[o] = z;
+            if (bary || dists) {
+                float b0 = -1.f, b1 = -1.f, b2 = -1.f, dd = -1.f;
+                if (f >= 0) {
+                    const unsigned int pk = s.fp[f];
+                    const int i0 = pk & 1023, i1 = (pk >> 10) & 1023, i2 = pk >> 20;
+                    const float x0 = s.vn[3 * i0], y0 = s.vn[3 * i0 + 1], z0 = s.vn[3 * i0 + 2];
+                    const float x1 = s.vn[3 * i1], y1 = s.vn[3 * i1 + 1], z1 = s.vn[3 * i1 + 2];
+                    const float x2 = s.vn[3 * i2], y2 = s.vn[3 * i2 + 1], z2 = s.vn[3 * i2 + 2];
+                    const float px = s.xs[tx0 + lx], py = s.ys[ty0 + ly];
+                    const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
+                    FragEval fe = eval_fragment(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
+                    b0 = fe.b0; b1 = fe.b1; b2 = fe.b2;
+                    float d01 = seg_dist_rn(px, py, x0, y0, x1, y1);
+                    float d02 = seg_dist_rn(px, py, x0, y0, x2, y2);
+                    float d12 = seg_dist_rn(px, py, x1, y1, x2, y2);
+                    float m = d01 < d02 ? d01 : d02;
+                    m = m < d12 ? m : d12;
+                    dd = -m;
+                }
+                if (bary) { bary[3 * o] = b0; bary[3 * o + 1] = b1; bary[3 * o + 2] = b2; }
+                if (dists) dists[o] = dd;
+            }
+        }
+    }
+    if (parts_tile) {
+        // fixed-order block reduction (the lists are dead by now, reuse their storage)
+        float* red = reinterpret_cast<float*>(s.items);
+        l_sum = warp_sum(l_sum);
+        l_cnt = warp_sum(l_cnt);
+        __syncthreads();
+        if (lane == 0) { red[2 * (tid >> 5)] = l_sum; red[2 * (tid >> 5) + 1] = l_cnt; }
+        __syncthreads();
+        if (tid == 0) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < RT_THREADS / 32; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+            float* out = parts_tile + ((size_t)mesh * gridDim.x + tile) * 2;
+            out[0] = a;
+            out[1] = b;
         }
     }
 }
 
+int dsf_raster_tiles(int R) { return ((R + RT_TW - 1) / RT_TW) * ((R + RT_TH - 1) / RT_TH); }
+
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
-                            cudaStream_t st) {
+                            const float* target, float thr, float* parts_tile, cudaStream_t st) {
     if (h->n_faces > RT_MAXF) {
         dsf_set_error("rasteriser supports at most %d faces (got %d)", RT_MAXF, h->n_faces);
         return DSF_ERR_UNSUPPORTED;
@@ -548,7 +575,7 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
     dim3 grid(tiles_x * tiles_y, n_mesh);
     raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
                                                       h->faces_packed, h->n_faces, view, xs, ys, img, p2f,
-                                                      zbuf, bary, dists);
+                                                      zbuf, bary, dists, target, thr, parts_tile);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -561,7 +588,7 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
     DSF_REQUIRE(n_mesh > 0 && n_mesh <= 65535, "n_mesh must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face,
-                                   zbuf, bary, dists, (cudaStream_t)stream);
+                                   zbuf, bary, dists, nullptr, 0.f, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,12 +597,15 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
 // the projection to camera space.
 // ------------------------------------------------------------------------------------------------
 #define RB_THREADS 256
+#define RB_CHUNK 16384      // pixels per pass; list entries are 16-bit offsets into the chunk
 
 __global__ void __launch_bounds__(RB_THREADS)
 raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const int* __restrict__ faces,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
-                  const int* __restrict__ p2f, const float* __restrict__ g_img, float* __restrict__ g_verts) {
+                  const int* __restrict__ p2f, const float* __restrict__ g_img, float* __restrict__ g_verts,
+                  const float* __restrict__ target, const float* __restrict__ img,
+                  const float* __restrict__ parts, float gscale, float thr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* svn = reinterpret_cast<float*>(smem_raw);
     float* sgn = svn + NVW * 3;
@@ -598,36 +628,61 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     const float zmax = vw.zc + vw.zh, zmin_c = vw.zc - vw.zh;
     const float inv_zh = 1.f / vw.zh;
     const int* pf = p2f + (size_t)mesh * R * R;
-    const float* gi = g_img + (size_t)mesh * R * R;
-    // Only ~20 % of the pixels are foreground: each warp compacts the live pixels of successive
-    // 32-pixel chunks into a private queue and runs the (long) gradient body on full warps.
-    __shared__ int s_queue[RB_THREADS / 32][64];
-    const int warp = tid >> 5, lane = tid & 31;
-    int* q = s_queue[warp];
-    int queued = 0;
+    // cotangent of the image: given explicitly, or the m2d loss gradient recomputed on the fly:
+    // d loss / d synth = gscale / (N_b + 1e-8) * sign(synth - real) on the union mask
+    const float* gi = g_img ? g_img + (size_t)mesh * R * R : nullptr;
+    const float* tg = target ? target + (size_t)mesh * R * R : nullptr;
+    const float* im = img ? img + (size_t)mesh * R * R : nullptr;
+    const float gk = parts ? gscale / (parts[2 * mesh + 1] + 1e-8f) : 0.f;
+    auto cotangent = [&](int k) -> float {
+        if (gi) return gi[k];
+        const float a = tg[k], c = im[k];
+        if (!(a < thr || c < thr)) return 0.f;
+        const float d = c - a;
+        return d > 0.f ? gk : (d < 0.f ? -gk : 0.f);
+    };
+    // Only ~20 % of the pixels are foreground.  Phase 1: the whole CTA streams pix_to_face with
+    // 128-bit loads and appends the foreground pixel ids of a 16384-pixel chunk to a shared list
+    // (warp-aggregated).  Phase 2: the list is consumed by full warps running the gradient body.
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(sys + R);
+    __shared__ int s_count;
+    const int lane = tid & 31;
     const int n_pix = R * R;
-    for (int base = warp * 32; base < n_pix || queued > 0; base += RB_THREADS) {
-        if (base < n_pix) {
-            const int k = base + lane;
-            const bool live = k < n_pix && pf[k] >= 0 && gi[k] != 0.f;
-            const unsigned int m = __ballot_sync(0xffffffffu, live);
-            if (live) q[queued + __popc(m & ((1u << lane) - 1u))] = k;
-            queued += __popc(m);
-            __syncwarp();
-            if (queued < 32 && base + RB_THREADS < n_pix) continue;
-        }
-        const int take = min(queued, 32);
-        const int k = lane < take ? q[lane] : -1;
-        const int carry = (lane + 32 < queued) ? q[lane + 32] : 0;
-        __syncwarp();
-        if (lane + 32 < queued) q[lane] = carry;
-        queued -= take;
-        __syncwarp();
+    for (int chunk0 = 0; chunk0 < n_pix; chunk0 += RB_CHUNK) {
+      const int chunk_n = min(RB_CHUNK, n_pix - chunk0);
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      for (int q0 = (tid & ~31) * 4; q0 < chunk_n; q0 += RB_THREADS * 4) {
+          const int k0 = q0 + lane * 4;                          // 4 consecutive pixels per lane
+          int4 f4 = make_int4(-1, -1, -1, -1);
+          if (k0 + 3 < chunk_n) {
+              f4 = *reinterpret_cast<const int4*>(pf + chunk0 + k0);   // R*R is a multiple of 4
+          } else {
+              if (k0 < chunk_n) f4.x = pf[chunk0 + k0];
+              if (k0 + 1 < chunk_n) f4.y = pf[chunk0 + k0 + 1];
+              if (k0 + 2 < chunk_n) f4.z = pf[chunk0 + k0 + 2];
+          }
+          const int n = (f4.x >= 0) + (f4.y >= 0) + (f4.z >= 0) + (f4.w >= 0);
+          int total;
+          const int excl = warp_excl_scan(n, lane, &total);
+          int base = 0;
+          if (lane == 0 && total > 0) base = atomicAdd(&s_count, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          int slot = base + excl;
+          if (f4.x >= 0) s_list[slot++] = (unsigned short)k0;
+          if (f4.y >= 0) s_list[slot++] = (unsigned short)(k0 + 1);
+          if (f4.z >= 0) s_list[slot++] = (unsigned short)(k0 + 2);
+          if (f4.w >= 0) s_list[slot++] = (unsigned short)(k0 + 3);
+      }
+      __syncthreads();
+      const int n_live = s_count;
+      for (int eb = tid & ~31; eb < n_live; eb += RB_THREADS) {
+        const int k = (eb + lane < n_live) ? chunk0 + (int)s_list[eb + lane] : -1;
         // every lane stays in the body (inactive ones carry zeros) so the warp can reduce per face
         bool act = k >= 0;
         const int kk = act ? k : 0;
         const int f = act ? pf[kk] : 0;
-        const float g = act ? gi[kk] : 0.f;
+        const float g = act ? cotangent(kk) : 0.f;
         const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
         const float x0 = svn[3 * i0], y0 = svn[3 * i0 + 1], z0 = svn[3 * i0 + 2];
         const float x1 = svn[3 * i1], y1 = svn[3 * i1 + 1], z1 = svn[3 * i1 + 2];
@@ -645,7 +700,7 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
         const float b0 = t0 * id, b1 = t1 * id, b2 = t2 * id;
         const float pz = b0 * z0 + b1 * z1 + b2 * z2;
         // gates of the forward epilogue: background fill and the [zmin,zmax] clamp pass no gradient
-        act = act && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
+        act = act && g != 0.f && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
         const float gz = act ? g * inv_zh : 0.f;
         const float gb0 = gz * z0, gb1 = gz * z1, gb2 = gz * z2;
         const float sgb = (gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
@@ -685,8 +740,9 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
             atomicAdd(&sgn[3 * i1], gv[3]); atomicAdd(&sgn[3 * i1 + 1], gv[4]); atomicAdd(&sgn[3 * i1 + 2], gv[5]);
             atomicAdd(&sgn[3 * i2], gv[6]); atomicAdd(&sgn[3 * i2 + 1], gv[7]); atomicAdd(&sgn[3 * i2 + 2], gv[8]);
         }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     float* go = g_verts + (size_t)mesh * NVW * 3;
     for (int v = tid; v < NVW; v += RB_THREADS) {
         float x = vm[3 * v], y = vm[3 * v + 1], z = vm[3 * v + 2];
@@ -706,10 +762,19 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
 
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
-                             int R, const int* p2f, const float* g_img, float* g_verts, cudaStream_t st) {
-    const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4;
+                             int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
+                             const float* img, const float* parts, float gscale, float thr, cudaStream_t st) {
+    const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK * 2;
+    static bool attr_set[16] = {};
+    int dev = 0;
+    DSF_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16 || !attr_set[dev]) {
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK * 2)));
+        if (dev < 16) attr_set[dev] = true;
+    }
     raster_bwd_kernel<<<n_mesh, RB_THREADS, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs,
-                                                        ys, p2f, g_img, g_verts);
+                                                        ys, p2f, g_img, g_verts, target, img, parts, gscale, thr);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -722,7 +787,7 @@ extern "C" int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* ve
     DSF_REQUIRE(n_mesh > 0, "n_mesh must be positive");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_backward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face,
-                                    g_img, g_verts_cam, (cudaStream_t)stream);
+                                    g_img, g_verts_cam, nullptr, nullptr, nullptr, 0.f, 0.f, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -803,6 +868,29 @@ depth_loss_grad_global_kernel(int n, const float* __restrict__ real, const float
         const float d = c - a;
         g_synth[(size_t)b * n + i] = m ? (d > 0.f ? k : (d < 0.f ? -k : 0.f)) : 0.f;
     }
+}
+
+// fold per-tile partial sums (written by the fused raster epilogue) into parts (B,2), fixed order
+__global__ void __launch_bounds__(LS_THREADS)
+fold_tile_parts_kernel(int B, int n_tiles, const float* __restrict__ parts_tile, float* __restrict__ parts) {
+    const int b = blockIdx.x * LS_THREADS + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f, c = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+        s += parts_tile[((size_t)b * n_tiles + t) * 2];
+        c += parts_tile[((size_t)b * n_tiles + t) * 2 + 1];
+    }
+    parts[2 * b] = s;
+    parts[2 * b + 1] = c;
+}
+
+int dsf_fold_loss_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
+                       cudaStream_t st) {
+    fold_tile_parts_kernel<<<(B + LS_THREADS - 1) / LS_THREADS, LS_THREADS, 0, st>>>(B, n_tiles, parts_tile, parts);
+    DSF_CHECK_LAUNCH();
+    depth_loss_totals_kernel<<<1, LS_THREADS, 0, st>>>(0, B, weight, parts, totals);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
 }
 
 int dsf_depth_loss_impl(int mode, int B, int R, const float* real, const float* synth, float thr, float weight,
