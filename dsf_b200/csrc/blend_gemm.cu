@@ -1,0 +1,221 @@
+// dsf_b200 - blend-shape contraction on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   forward   v_posed(B x 2336) = [beta | Rs - I](B x 148) . [shapedirs ; posedirs](148 x 2336) + v_template
+//             (render_model/mano_layer.py:586 and :613 as one GEMM)
+//   backward  g_X(B x 148)      = g_vposed(B x 2336) . basis^T
+//
+// Vertices must match the fp32 reference to 1e-5, which single-pass TF32 (10-bit mantissa) cannot
+// give, so every product is computed error-compensated ("3xTF32"):
+//       a.b  ~=  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi,     a_hi = a with the low 13 mantissa bits cleared
+// The basis is split into hi/lo once on the host; the activation tile is split on the fly while
+// it is written into shared memory.  One CTA = one 128-row tile: tcgen05.mma (kind::tf32, M=128,
+// N=128 or 160, K=8) issued by a single thread, fp32 accumulator in TMEM, operands in shared memory
+// in the canonical no-swizzle K-major core-matrix layout, two smem stages guarded by mbarriers that
+// tcgen05.commit arrives on, epilogue tcgen05.ld -> registers -> global.
+#include "common.cuh"
+
+#define GM 128            // rows (hands) per CTA = UMMA M
+#define GKB 32            // k elements per stage (one 128-byte row of fp32)
+#define G_THREADS 128
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: 8 x 16-byte core matrices; LBO = 128 B between K-adjacent core matrices,
+// SBO = 1024 B between 8-row groups (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// float index of element (row r, k) inside an operand tile of GKB columns
+__device__ __forceinline__ int tile_idx(int r, int k) { return ((r >> 3) * (GKB / 4) + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS)
+tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bh,
+                   const float* __restrict__ Bl, int ldb, float* __restrict__ C, int ldc, long split_stride,
+                   const float* __restrict__ bias, int kb_per_split) {
+    constexpr int TM_COLS = BN <= 128 ? 128 : 256;
+    constexpr int A_FLOATS = GM * GKB, B_FLOATS = BN * GKB;
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    float* sA[2] = {reinterpret_cast<float*>(gsm), reinterpret_cast<float*>(gsm) + A_FLOATS + B_FLOATS};
+    float* sB[2] = {sA[0] + A_FLOATS, sA[1] + A_FLOATS};
+    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * BN;
+    const int nkb_total = (K + GKB - 1) / GKB;
+    const int kb_lo = blockIdx.z * kb_per_split, kb_hi = min(nkb_total, kb_lo + kb_per_split);
+    const int nkb = max(0, kb_hi - kb_lo);
+    const int n_steps = 3 * nkb;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(TM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+
+    for (int step = 0; step < n_steps; ++step) {
+        const int s = step & 1;
+        const int pass = step / nkb;                  // 0: a_hi.b_hi   1: a_hi.b_lo   2: a_lo.b_hi
+        const int k0 = (kb_lo + step % nkb) * GKB;
+        if (step >= 2) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((step >> 1) - 1) & 1));
+        // ---- stage the operand tiles: thread -> (8-row group, 16-byte k chunk), conflict-free stores
+        const float* Bsrc = pass == 1 ? Bl : Bh;
+        float4 av[GM * GKB / 4 / G_THREADS];
+        float4 bv[BN * GKB / 4 / G_THREADS];
+#pragma unroll
+        for (int i = 0; i < GM * GKB / 4 / G_THREADS; ++i) {
+            const int q = i * G_THREADS + tid;
+            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
+            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M && k0 + k < K) av[i] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + k);
+        }
+#pragma unroll
+        for (int i = 0; i < BN * GKB / 4 / G_THREADS; ++i) {
+            const int q = i * G_THREADS + tid;
+            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
+            bv[i] = __ldg(reinterpret_cast<const float4*>(Bsrc + (size_t)(n0 + r) * ldb + k0 + k));   // zero padded
+        }
+#pragma unroll
+        for (int i = 0; i < GM * GKB / 4 / G_THREADS; ++i) {
+            const int q = i * G_THREADS + tid;
+            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
+            float4 v = av[i];
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            if (pass == 2) h = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            *reinterpret_cast<float4*>(sA[s] + tile_idx(r, k)) = h;
+        }
+#pragma unroll
+        for (int i = 0; i < BN * GKB / 4 / G_THREADS; ++i) {
+            const int q = i * G_THREADS + tid;
+            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
+            *reinterpret_cast<float4*>(sB[s] + tile_idx(r, k)) = bv[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t a_base = smem_u32(sA[s]), b_base = smem_u32(sB[s]);
+#pragma unroll
+            for (int j = 0; j < GKB / 8; ++j) {
+                const uint64_t da = make_smem_desc(a_base + j * 256), db = make_smem_desc(b_base + j * 256);
+                const uint32_t acc = (step > 0 || j > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem),
+                    "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+                    : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&mbar[s]))
+                         : "memory");
+        }
+    }
+    // ---- epilogue: wait for the last commit (covers every earlier MMA), TMEM -> registers -> global
+    if (n_steps > 0) {
+        const int last = n_steps - 1;
+        mbar_wait(smem_u32(&mbar[last & 1]), (uint32_t)((last >> 1) & 1));
+        if (n_steps > 1) mbar_wait(smem_u32(&mbar[(last - 1) & 1]), (uint32_t)(((last - 1) >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const int row = m0 + warp * 32 + lane;
+    float* crow = C + (size_t)blockIdx.z * split_stride + (size_t)row * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        if (n_steps > 0) {
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        if (row < M) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const int n = n0 + c0 + i;
+                if (n < N) {          // N and the column offsets are multiples of 4
+                    float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                           __uint_as_float(v[i + 3]));
+                    if (bias) {
+                        const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + n));
+                        o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
+                    }
+                    *reinterpret_cast<float4*>(crow + n) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS));
+    }
+}
+
+template <int BN>
+static int launch_tf32x3(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
+                         float* C, int ldc, long split_stride, const float* bias, int n_split, cudaStream_t st) {
+    const size_t smem = (size_t)2 * (GM + BN) * GKB * sizeof(float);
+    static bool attr_set[16] = {};
+    int dev = 0;
+    DSF_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16 || !attr_set[dev]) {
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 16) attr_set[dev] = true;
+    }
+    const int nkb = (K + GKB - 1) / GKB;
+    const int kbs = (nkb + n_split - 1) / n_split;
+    dim3 grid((N + BN - 1) / BN, (M + GM - 1) / GM, n_split);
+    tf32x3_gemm_kernel<BN><<<grid, G_THREADS, smem, st>>>(M, N, K, A, lda, Bh, Bl, ldb, C, ldc, split_stride, bias, kbs);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// forward: C (M x 2336) = A (M x 148) . basis + bias; Bh/Bl = basis^T split, (2432 x 160) zero padded
+int dsf_blend_forward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
+                           const float* bias, cudaStream_t st) {
+    return launch_tf32x3<128>(M, NP, KP, A, lda, Bh, Bl, BLEND_KPAD, C, ldc, 0, bias, 1, st);
+}
+
+// backward: BLEND_SPLITS partial products C_z (M x 148) = A[:, kz] (M x 2336) . basis^T[kz, :];
+// Bh/Bl = basis split, (160 x 2336); the consumer sums the partials in a fixed order
+int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
+                            long split_stride, cudaStream_t st) {
+    return launch_tf32x3<160>(M, KP, NP, A, lda, Bh, Bl, NP, C, ldc, split_stride, nullptr, BLEND_SPLITS, st);
+}

@@ -13,6 +13,10 @@
 #define NJOUT DSF_NJOUT
 #define KP 148           // blend-shape K: 10 beta + 135 pose feature, padded to a multiple of 4
 #define NP 2336          // 778*3 = 2334 padded to a multiple of 4
+#define BLEND_KPAD 160    // KP rounded up to the 32-float k block of the tensor-core GEMM
+#define BLEND_NPAD 2432   // NP rounded up to the 128-column tile
+#define BLEND_BN_BWD 160  // KP rounded up to a legal UMMA N
+#define BLEND_SPLITS 8    // split-K factor of the backward contraction
 #define RJ_STRIDE 32     // per joint: R[9] Gr[9] Gt[3] J[3] At[3] ang[3] pad[2]
 #define RJ_R 0
 #define RJ_GR 9
@@ -28,12 +32,14 @@
 #define WS_RJ (WS_VP + NP)
 #define WS_GVP (WS_RJ + NJ * RJ_STRIDE)
 #define WS_GA (WS_GVP + NP)
-#define WS_GX (WS_GA + NJ * 12)
-#define WS_PER_HAND (WS_GX + KP)
+#define WS_GX (WS_GA + NJ * 12)          // BLEND_SPLITS split-K partials of g_X, KP floats each
+#define WS_PER_HAND (WS_GX + BLEND_SPLITS * KP)
 
 struct DsfMano {
-    float* Dmat;   // (KP, NP)  rows 0-9 shapedirs, 10-144 posedirs, rest 0
-    float* DmatT;  // (NP, KP)
+    float* BTh;    // (BLEND_NPAD, BLEND_KPAD) basis^T, tf32 hi part, zero padded   (forward B operand)
+    float* BTl;    //                          basis^T, lo part
+    float* Bh;     // (BLEND_BN_BWD, NP)       basis, hi part                         (backward B operand)
+    float* Bl;     //                          basis, lo part
     float* vt;     // (NP) v_template, flat, zero padded
     float* W;      // (778,16) skin weights
     float* comp;   // (45,45)

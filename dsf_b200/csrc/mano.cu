@@ -76,14 +76,30 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
         }
     }
 
-    std::vector<float> D((size_t)KP * NP, 0.f), DT((size_t)NP * KP, 0.f), vt(NP, 0.f);
+    // blend basis D (148 x 2336): rows 0-9 shapedirs, 10-144 posedirs; split into tf32 hi / lo parts
+    // once, in the two operand orientations the tensor-core GEMMs read (blend_gemm.cu)
+    std::vector<float> D((size_t)KP * NP, 0.f), vt(NP, 0.f);
     for (int k = 0; k < 10; ++k)
         for (int n = 0; n < NV * 3; ++n) D[(size_t)k * NP + n] = host->shapedirs[(size_t)k * NV * 3 + n];
     for (int k = 0; k < 135; ++k)
         for (int n = 0; n < NV * 3; ++n) D[(size_t)(10 + k) * NP + n] = host->posedirs[(size_t)k * NV * 3 + n];
-    for (int k = 0; k < KP; ++k)
-        for (int n = 0; n < NP; ++n) DT[(size_t)n * KP + k] = D[(size_t)k * NP + n];
     for (int n = 0; n < NV * 3; ++n) vt[n] = host->v_template[n];
+    std::vector<float> BTh((size_t)BLEND_NPAD * BLEND_KPAD, 0.f), BTl(BTh.size(), 0.f);
+    std::vector<float> Bh((size_t)BLEND_BN_BWD * NP, 0.f), Bl(Bh.size(), 0.f);
+    for (int k = 0; k < KP; ++k)
+        for (int n = 0; n < NP; ++n) {
+            const float v = D[(size_t)k * NP + n];
+            uint32_t bits;
+            memcpy(&bits, &v, 4);
+            bits &= 0xFFFFE000u;
+            float hi;
+            memcpy(&hi, &bits, 4);
+            const float lo = v - hi;
+            BTh[(size_t)n * BLEND_KPAD + k] = hi;
+            BTl[(size_t)n * BLEND_KPAD + k] = lo;
+            Bh[(size_t)k * NP + n] = hi;
+            Bl[(size_t)k * NP + n] = lo;
+        }
 
     // rest joints as an affine function of beta: J = Jt + sum_b beta_b JS[b]   (mano_layer.py:586-591)
     std::vector<float> Jt(NJ * 3), JS(10 * NJ * 3);
@@ -132,8 +148,10 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     dsf_build_collision_mask(mask.data());
 
     int rc = 0;
-    rc |= upload(&h->Dmat, D.data(), D.size());
-    rc |= upload(&h->DmatT, DT.data(), DT.size());
+    rc |= upload(&h->BTh, BTh.data(), BTh.size());
+    rc |= upload(&h->BTl, BTl.data(), BTl.size());
+    rc |= upload(&h->Bh, Bh.data(), Bh.size());
+    rc |= upload(&h->Bl, Bl.data(), Bl.size());
     rc |= upload(&h->vt, vt.data(), vt.size());
     rc |= upload(&h->W, host->weights, (size_t)NV * NJ);
     rc |= upload(&h->comp, host->hands_comp, 45 * 45);
@@ -164,7 +182,7 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
 
 extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
-    void* ptrs[] = {h->Dmat, h->DmatT, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
+    void* ptrs[] = {h->BTh, h->BTl, h->Bh, h->Bl, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
                     h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx, h->wj_w, h->faces, h->faces_packed,
                     h->coll_mask};
     for (void* p : ptrs)
@@ -300,66 +318,11 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: fp32 SIMT GEMM  C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]); all leading dims multiples of 4.
-// Used for the blend-shape contraction (:586,:613) and its transpose in backward.
-// ------------------------------------------------------------------------------------------------
-#define GB_M 64
-#define GB_N 64
-#define GB_K 16
-
-__global__ void __launch_bounds__(256)
-sgemm_bias_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
-                  int ldb, float* __restrict__ C, int ldc, const float* __restrict__ bias) {
-    __shared__ float As[GB_K][GB_M + 4];
-    __shared__ float Bs[GB_K][GB_N + 4];
-    const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
-    const int tr = tid / 16, tc = tid % 16;     // 16x16 threads, 4x4 outputs each
-    float acc[4][4] = {};
-    const int a_row = tid / 4, a_k4 = (tid % 4) * 4;        // A tile: 64 rows x 16 k
-    const int b_k = tid / 16, b_n4 = (tid % 16) * 4;        // B tile: 16 k x 64 cols
-    for (int k0 = 0; k0 < K; k0 += GB_K) {
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
-        if (m0 + a_row < M && k0 + a_k4 < K)
-            av = *reinterpret_cast<const float4*>(A + (size_t)(m0 + a_row) * lda + k0 + a_k4);
-        if (k0 + b_k < K && n0 + b_n4 < N)
-            bv = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + b_k) * ldb + n0 + b_n4);
-        As[a_k4][a_row] = av.x; As[a_k4 + 1][a_row] = av.y; As[a_k4 + 2][a_row] = av.z; As[a_k4 + 3][a_row] = av.w;
-        *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = bv;
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < GB_K; ++kk) {
-            float4 a = *reinterpret_cast<const float4*>(&As[kk][tr * 4]);
-            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tc * 4]);
-            float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(ar[i], br[jn], acc[i][jn]);
-        }
-        __syncthreads();
-    }
-    const int n = n0 + tc * 4;
-    if (n < N) {
-        float4 bz = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int m = m0 + tr * 4 + i;
-            if (m < M)
-                *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) =
-                    make_float4(acc[i][0] + bz.x, acc[i][1] + bz.y, acc[i][2] + bz.z, acc[i][3] + bz.w);
-        }
-    }
-}
-
-static int launch_sgemm(int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, float* C,
-                        int ldc, const float* bias, cudaStream_t st) {
-    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
-    sgemm_bias_kernel<<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, bias);
-    DSF_CHECK_LAUNCH();
-    return DSF_OK;
-}
+// K2: the blend-shape contraction runs on the tensor cores, see blend_gemm.cu
+int dsf_blend_forward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
+                           const float* bias, cudaStream_t st);
+int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
+                            long split_stride, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // K3: skinning kernel - one CTA per hand.  LBS (:619-629), joint regression (:630-633), wrist-cap
@@ -695,7 +658,12 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     if (j >= 1) {
         const float* gx = wsh + WS_GX + 10 + 9 * (j - 1);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) gR[e] += gx[e];
+        for (int e = 0; e < 9; ++e) {
+            float a = 0.f;
+#pragma unroll
+            for (int z = 0; z < BLEND_SPLITS; ++z) a += gx[z * KP + e];     // fixed order: deterministic
+            gR[e] += a;
+        }
     }
     __syncwarp();
     if (j == 0 && p.quat_dim == 4) {
@@ -722,7 +690,9 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
             g.theta[(size_t)hh * g.ld_theta + k] = a;
         }
         if (j < 10) {                                  // direct blend-shape term + rest-joint term
-            float a = wsh[WS_GX + j];
+            float a = 0.f;
+#pragma unroll
+            for (int z = 0; z < BLEND_SPLITS; ++z) a += wsh[WS_GX + z * KP + j];
             for (int i = 0; i < NJ; ++i) {
                 const float* gj = &s_acc[hl][i][12];
                 const float* js = JS + (j * NJ + i) * 3;
@@ -752,7 +722,7 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
                                                                               h->JS, topo, ws);
     DSF_CHECK_LAUNCH();
     // v_posed = v_template + [beta | Rs - I] . [shapedirs ; posedirs]
-    rc = launch_sgemm(B, NP, KP, ws + WS_X, WS_PER_HAND, h->Dmat, NP, ws + WS_VP, WS_PER_HAND, h->vt, st);
+    rc = dsf_blend_forward_gemm(B, ws + WS_X, WS_PER_HAND, h->BTh, h->BTl, ws + WS_VP, WS_PER_HAND, h->vt, st);
     if (rc) return rc;
     mano_skin_kernel<<<B, SKIN_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
                                            unit_scale, verts, joints, Rs);
@@ -771,8 +741,8 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
                                               unit_scale, verts, joints, g_verts, g_joints,
                                               p->cam ? g->cam : nullptr, g->ld_cam);
     DSF_CHECK_LAUNCH();
-    // g_X = g_vposed . Dmat^T
-    rc = launch_sgemm(B, KP, NP, ws + WS_GVP, WS_PER_HAND, h->DmatT, KP, ws + WS_GX, WS_PER_HAND, nullptr, st);
+    // g_X = g_vposed . basis^T as BLEND_SPLITS split-K partials (summed by the pose backward kernel)
+    rc = dsf_blend_backward_gemm(B, ws + WS_GVP, WS_PER_HAND, h->Bh, h->Bl, ws + WS_GX, WS_PER_HAND, KP, st);
     if (rc) return rc;
     mano_pose_bwd_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, *g, h->comp, h->JS,
                                                                                   topo, ws);
