@@ -7,8 +7,8 @@
 // Vertices must match the fp32 reference to 1e-5, which single-pass TF32 (10-bit mantissa) cannot
 // give, so every product is computed error-compensated ("3xTF32"):
 //       a.b  ~=  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi,     a_hi = a with the low 13 mantissa bits cleared
-// The basis is split into hi/lo once on the host; the activation tile is split on the fly while
-// it is written into shared memory.  One CTA = one 128-row tile: tcgen05.mma (kind::tf32, M=128,
+// The basis is split into hi/lo once on the host (cp.async straight into shared memory); the
+// activation tile is read once per k block and split on the fly into a hi and a lo operand tile.  One CTA = one 128-row tile: tcgen05.mma (kind::tf32, M=128,
 // N=128 or 160, K=8) issued by a single thread, fp32 accumulator in TMEM, operands in shared memory
 // in the canonical no-swizzle K-major core-matrix layout, two smem stages guarded by mbarriers that
 // tcgen05.commit arrives on, epilogue tcgen05.ld -> registers -> global.
@@ -44,6 +44,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "D_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ void issue_mma(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t idesc, bool first) {
+#pragma unroll
+    for (int j = 0; j < GKB / 8; ++j) {
+        const uint64_t da = make_smem_desc(a_base + j * 256), db = make_smem_desc(b_base + j * 256);
+        const uint32_t acc = (first && j == 0) ? 0u : 1u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+            : "memory");
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS)
 tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bh,
@@ -51,17 +68,17 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
                    const float* __restrict__ bias, int kb_per_split) {
     constexpr int TM_COLS = BN <= 128 ? 128 : 256;
     constexpr int A_FLOATS = GM * GKB, B_FLOATS = BN * GKB;
+    constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;       // A_hi, A_lo, B_hi, B_lo
+    constexpr int A_IT = GM * GKB / 4 / G_THREADS, B_IT = BN * GKB / 4 / G_THREADS;
     extern __shared__ __align__(1024) unsigned char gsm[];
-    float* sA[2] = {reinterpret_cast<float*>(gsm), reinterpret_cast<float*>(gsm) + A_FLOATS + B_FLOATS};
-    float* sB[2] = {sA[0] + A_FLOATS, sA[1] + A_FLOATS};
+    float* stage0 = reinterpret_cast<float*>(gsm);
     __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * BN;
     const int nkb_total = (K + GKB - 1) / GKB;
     const int kb_lo = blockIdx.z * kb_per_split, kb_hi = min(nkb_total, kb_lo + kb_per_split);
-    const int nkb = max(0, kb_hi - kb_lo);
-    const int n_steps = 3 * nkb;
+    const int n_steps = max(0, kb_hi - kb_lo);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -80,62 +97,61 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
 
-    for (int step = 0; step < n_steps; ++step) {
-        const int s = step & 1;
-        const int pass = step / nkb;                  // 0: a_hi.b_hi   1: a_hi.b_lo   2: a_lo.b_hi
-        const int k0 = (kb_lo + step % nkb) * GKB;
-        if (step >= 2) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((step >> 1) - 1) & 1));
-        // ---- stage the operand tiles: thread -> (8-row group, 16-byte k chunk), conflict-free stores
-        const float* Bsrc = pass == 1 ? Bl : Bh;
-        float4 av[GM * GKB / 4 / G_THREADS];
-        float4 bv[BN * GKB / 4 / G_THREADS];
+    // thread -> (8-row group, 16-byte k chunk): conflict-free 16-byte shared stores
+    auto load_a = [&](int k0, float4* av) {
 #pragma unroll
-        for (int i = 0; i < GM * GKB / 4 / G_THREADS; ++i) {
+        for (int i = 0; i < A_IT; ++i) {
             const int q = i * G_THREADS + tid;
             const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
             av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m0 + r < M && k0 + k < K) av[i] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + k);
         }
+    };
+    float4 av[A_IT];
+    if (n_steps > 0) load_a(kb_lo * GKB, av);
+
+    for (int step = 0; step < n_steps; ++step) {
+        const int s = step & 1;
+        const int k0 = (kb_lo + step) * GKB;
+        float* sAh = stage0 + s * STAGE_FLOATS;
+        float* sAl = sAh + A_FLOATS;
+        float* sBh = sAl + A_FLOATS;
+        float* sBl = sBh + B_FLOATS;
+        if (step >= 2) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((step >> 1) - 1) & 1));
+        // basis tiles (already split on the host, zero padded): asynchronous 16-byte copies
 #pragma unroll
-        for (int i = 0; i < BN * GKB / 4 / G_THREADS; ++i) {
+        for (int i = 0; i < B_IT; ++i) {
             const int q = i * G_THREADS + tid;
             const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            bv[i] = __ldg(reinterpret_cast<const float4*>(Bsrc + (size_t)(n0 + r) * ldb + k0 + k));   // zero padded
+            const size_t go = (size_t)(n0 + r) * ldb + k0 + k;
+            cp_async16(sBh + tile_idx(r, k), Bh + go);
+            cp_async16(sBl + tile_idx(r, k), Bl + go);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // activation tile: split into tf32 hi / lo on the way into shared memory
 #pragma unroll
-        for (int i = 0; i < GM * GKB / 4 / G_THREADS; ++i) {
+        for (int i = 0; i < A_IT; ++i) {
             const int q = i * G_THREADS + tid;
             const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            float4 v = av[i];
+            const float4 v = av[i];
             float4 h;
             h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            if (pass == 2) h = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            *reinterpret_cast<float4*>(sA[s] + tile_idx(r, k)) = h;
+            *reinterpret_cast<float4*>(sAh + tile_idx(r, k)) = h;
+            *reinterpret_cast<float4*>(sAl + tile_idx(r, k)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         }
-#pragma unroll
-        for (int i = 0; i < BN * GKB / 4 / G_THREADS; ++i) {
-            const int q = i * G_THREADS + tid;
-            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            *reinterpret_cast<float4*>(sB[s] + tile_idx(r, k)) = bv[i];
-        }
+        if (step + 1 < n_steps) load_a(k0 + GKB, av);          // prefetch the next activation tile
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t a_base = smem_u32(sA[s]), b_base = smem_u32(sB[s]);
-#pragma unroll
-            for (int j = 0; j < GKB / 8; ++j) {
-                const uint64_t da = make_smem_desc(a_base + j * 256), db = make_smem_desc(b_base + j * 256);
-                const uint32_t acc = (step > 0 || j > 0) ? 1u : 0u;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem),
-                    "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
-                    : "memory");
-            }
+            const uint32_t ah = smem_u32(sAh), al = smem_u32(sAl), bh = smem_u32(sBh), bl = smem_u32(sBl);
+            issue_mma(tmem, ah, bh, idesc, step == 0);      // a_hi . b_hi
+            issue_mma(tmem, ah, bl, idesc, false);          // a_hi . b_lo
+            issue_mma(tmem, al, bh, idesc, false);          // a_lo . b_hi
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              smem_u32(&mbar[s]))
                          : "memory");
@@ -191,7 +207,7 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
 template <int BN>
 static int launch_tf32x3(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
                          float* C, int ldc, long split_stride, const float* bias, int n_split, cudaStream_t st) {
-    const size_t smem = (size_t)2 * (GM + BN) * GKB * sizeof(float);
+    const size_t smem = (size_t)2 * 2 * (GM + BN) * GKB * sizeof(float);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
