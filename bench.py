@@ -238,7 +238,7 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         ms = time_region(one_step, args.steps)
         if args.steps * ms < 1500:      # keep the sampler alive long enough to see clocks under load
-            time_region(one_step, int(1500 / max(ms, 1e-3)) + 1)
+            time_region(step.step, int(1500 / max(ms, 1e-3)) + 1)    # local work only: no collective
     if world > 1:
         torch.distributed.barrier()
     ms = D.max_over_ranks(ms, dev)

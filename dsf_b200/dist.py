@@ -8,6 +8,7 @@ The helpers work on any torch.distributed backend (NCCL on the box, gloo in the 
 """
 from __future__ import annotations
 
+import datetime
 import os
 
 import torch
@@ -36,7 +37,8 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=180))
     return rank, world, local
 
 
