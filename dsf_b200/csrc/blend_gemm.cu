@@ -231,7 +231,15 @@ int dsf_blend_forward_gemm(int M, const float* A, int lda, const float* Bh, cons
 
 // backward: BLEND_SPLITS partial products C_z (M x 148) = A[:, kz] (M x 2336) . basis^T[kz, :];
 // Bh/Bl = basis split, (160 x 2336); the consumer sums the partials in a fixed order
+int dsf_blend_backward_splits(int M) {
+    // enough CTAs to cover the chip: (M / 128) row tiles x splits ~ 148 SMs, within [4, BLEND_SPLITS]
+    const int m_tiles = (M + GM - 1) / GM;
+    int s = 148 / m_tiles;
+    return s < 4 ? 4 : (s > BLEND_SPLITS ? BLEND_SPLITS : s);
+}
+
 int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
                             long split_stride, cudaStream_t st) {
-    return launch_tf32x3<160>(M, KP, NP, A, lda, Bh, Bl, NP, C, ldc, split_stride, nullptr, BLEND_SPLITS, st);
+    return launch_tf32x3<160>(M, KP, NP, A, lda, Bh, Bl, NP, C, ldc, split_stride, nullptr,
+                              dsf_blend_backward_splits(M), st);
 }

@@ -16,7 +16,7 @@
 #define BLEND_KPAD 160    // KP rounded up to the 32-float k block of the tensor-core GEMM
 #define BLEND_NPAD 2432   // NP rounded up to the 128-column tile
 #define BLEND_BN_BWD 160  // KP rounded up to a legal UMMA N
-#define BLEND_SPLITS 4    // split-K factor of the backward contraction
+#define BLEND_SPLITS 16   // maximum split-K factor of the backward contraction (workspace slots)
 #define RJ_STRIDE 32     // per joint: R[9] Gr[9] Gt[3] J[3] At[3] ang[3] pad[2]
 #define RJ_R 0
 #define RJ_GR 9

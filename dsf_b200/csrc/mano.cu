@@ -165,7 +165,7 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     rc |= upload(&h->wj_idx, widx.data(), widx.size());
     rc |= upload(&h->wj_w, wval.data(), wval.size());
     rc |= upload(&h->faces, host->faces, (size_t)host->n_faces * 3);
-    std::vector<unsigned int> fpk(host->n_faces);
+    std::vector<unsigned int> fpk((host->n_faces + 3) & ~3, 0u);     // padded to 16 bytes for bulk copies
     for (int f = 0; f < host->n_faces; ++f)
         fpk[f] = (unsigned)host->faces[3 * f] | ((unsigned)host->faces[3 * f + 1] << 10) |
                  ((unsigned)host->faces[3 * f + 2] << 20);
@@ -323,6 +323,7 @@ int dsf_blend_forward_gemm(int M, const float* A, int lda, const float* Bh, cons
                            const float* bias, cudaStream_t st);
 int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
                             long split_stride, cudaStream_t st);
+int dsf_blend_backward_splits(int M);
 
 // ------------------------------------------------------------------------------------------------
 // K3: skinning kernel - one CTA per hand.  LBS (:619-629), joint regression (:630-633), wrist-cap
@@ -585,7 +586,7 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(POSE_HPB* NJ)
 mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __restrict__ comp,
-                     const float* __restrict__ JS, ChainTopo topo, const float* __restrict__ ws) {
+                     const float* __restrict__ JS, ChainTopo topo, const float* __restrict__ ws, int n_split) {
     __shared__ float s_acc[POSE_HPB][NJ][15];   // gGr[9] gGt[3] gJ[3]
     __shared__ float s_gang[POSE_HPB][48];
     const int hl = threadIdx.x / NJ;
@@ -660,8 +661,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
             float a = 0.f;
-#pragma unroll
-            for (int z = 0; z < BLEND_SPLITS; ++z) a += gx[z * KP + e];     // fixed order: deterministic
+            for (int z = 0; z < n_split; ++z) a += gx[z * KP + e];     // fixed order: deterministic
             gR[e] += a;
         }
     }
@@ -691,8 +691,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
         }
         if (j < 10) {                                  // direct blend-shape term + rest-joint term
             float a = 0.f;
-#pragma unroll
-            for (int z = 0; z < BLEND_SPLITS; ++z) a += wsh[WS_GX + z * KP + j];
+            for (int z = 0; z < n_split; ++z) a += wsh[WS_GX + z * KP + j];
             for (int i = 0; i < NJ; ++i) {
                 const float* gj = &s_acc[hl][i][12];
                 const float* js = JS + (j * NJ + i) * 3;
@@ -745,7 +744,7 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
     rc = dsf_blend_backward_gemm(B, ws + WS_GVP, WS_PER_HAND, h->Bh, h->Bl, ws + WS_GX, WS_PER_HAND, KP, st);
     if (rc) return rc;
     mano_pose_bwd_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, *g, h->comp, h->JS,
-                                                                                  topo, ws);
+                                                                                  topo, ws, dsf_blend_backward_splits(B));
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

@@ -362,7 +362,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
-                  float thr, float* __restrict__ parts_tile) {
+                  float thr, float* __restrict__ parts_tile, int use_tma) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RasterSmem s = carve_smem(smem_raw, R, F);
     const int mesh = blockIdx.y;
@@ -372,16 +372,60 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const int tid = threadIdx.x, lane = tid & 31;
     const ViewRec vw = load_view(view + (size_t)mesh * VIEW);
 
-    for (int i = tid; i < R; i += RT_THREADS) {
-        s.xs[i] = xs_g[(size_t)mesh * R + i];
-        s.ys[i] = ys_g[(size_t)mesh * R + i];
-    }
-    for (int i = tid; i < F; i += RT_THREADS) s.fp[i] = faces_packed[i];
     const float* vm = verts + (size_t)mesh * NVW * 3;
     const float* ps = place_scale ? place_scale + 3 * mesh : nullptr;
     const float* po = place_off ? place_off + 3 * mesh : nullptr;
-    for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(vm + 3 * v, ps, po, vw, s.vn + 3 * v);
-    {
+    if (use_tma) {
+        // Stage this mesh's inputs with the TMA engine (cp.async.bulk, SASS UBLKCP): sample grids,
+        // packed triangle list and the raw vertex block (16-byte aligned window around the 9348-byte
+        // row, landed in the not-yet-used item list) - one thread issues, an mbarrier collects the bytes.
+        __shared__ __align__(8) unsigned long long tma_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+        const size_t v_off = (size_t)mesh * NVW * 3 * sizeof(float);
+        const uint32_t v_shift = (uint32_t)(v_off & 15);
+        const uint32_t v_bytes = (v_shift + NVW * 3 * (uint32_t)sizeof(float) + 15u) & ~15u;
+        const uint32_t g_bytes = (uint32_t)R * 4u, f_bytes = (uint32_t)((F + 3) & ~3) * 4u;
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"(2 * g_bytes + f_bytes + v_bytes)
+                         : "memory");
+            const char* vsrc = reinterpret_cast<const char*>(verts) + (v_off - v_shift);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s.xs)),
+                         "l"(xs_g + (size_t)mesh * R), "r"(g_bytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s.ys)),
+                         "l"(ys_g + (size_t)mesh * R), "r"(g_bytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s.fp)),
+                         "l"(faces_packed), "r"(f_bytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s.items)),
+                         "l"(vsrc), "r"(v_bytes), "r"(bar)
+                         : "memory");
+        }
+        {   // z-buffer clear overlaps the copies
+            ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s.key);
+            for (int i = tid; i < RT_TW * RT_TH / 2; i += RT_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
+        }
+        __syncthreads();                                   // barrier initialised before anyone polls it
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n" ::"r"(bar)
+            : "memory");
+        const float* raw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(s.items) + v_shift);
+        for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(raw + 3 * v, ps, po, vw, s.vn + 3 * v);
+    } else {
+        for (int i = tid; i < R; i += RT_THREADS) {
+            s.xs[i] = xs_g[(size_t)mesh * R + i];
+            s.ys[i] = ys_g[(size_t)mesh * R + i];
+        }
+        for (int i = tid; i < F; i += RT_THREADS) s.fp[i] = faces_packed[i];
+        for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(vm + 3 * v, ps, po, vw, s.vn + 3 * v);
         ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s.key);
         for (int i = tid; i < RT_TW * RT_TH / 2; i += RT_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
     }
@@ -573,10 +617,13 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
                                             (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
         if (dev < 16) attr_set[dev] = true;
     }
+    // bulk (TMA) staging needs 16-byte aligned sources and sizes; anything else takes plain loads
+    const int use_tma = (R % 4 == 0) && ((uintptr_t)verts % 16 == 0) && ((uintptr_t)xs % 16 == 0) &&
+                        ((uintptr_t)ys % 16 == 0);
     dim3 grid(tiles_x * tiles_y, n_mesh);
     raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
                                                       h->faces_packed, h->n_faces, view, xs, ys, img, p2f,
-                                                      zbuf, bary, dists, target, thr, parts_tile);
+                                                      zbuf, bary, dists, target, thr, parts_tile, use_tma);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -597,9 +644,11 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
 // perspective-correct barycentrics to the three NDC vertices (shared-memory atomics), then through
 // the projection to camera space.
 // ------------------------------------------------------------------------------------------------
-#define RB_THREADS 256
 #define RB_CHUNK 16384      // pixels per pass; list entries are 16-bit offsets into the chunk
 
+// RB_THREADS: 256 keeps more CTAs (hands) in flight for large batches, 512 halves the per-hand latency
+// when the batch does not fill the GPU anyway
+template <int RB_THREADS>
 __global__ void __launch_bounds__(RB_THREADS)
 raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const int* __restrict__ faces,
@@ -770,16 +819,21 @@ int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, c
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
                              const float* img, const float* parts, float gscale, float thr, cudaStream_t st) {
     const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK * 2;
+    const int max_smem = (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK * 2);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 16 || !attr_set[dev]) {
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK * 2)));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         if (dev < 16) attr_set[dev] = true;
     }
-    raster_bwd_kernel<<<n_mesh, RB_THREADS, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs,
-                                                        ys, p2f, g_img, g_verts, target, img, parts, gscale, thr);
+    if (n_mesh < 2048)
+        raster_bwd_kernel<512><<<n_mesh, 512, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
+                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr);
+    else
+        raster_bwd_kernel<256><<<n_mesh, 256, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
+                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
