@@ -273,7 +273,7 @@ struct RasterSmem {
     unsigned int* fp;          // F packed vertex ids
     unsigned int* items;       // RT_CAP
     unsigned int* cands;       // RT_CAP
-    int* counters;             // [0] items, [1] cands
+    int* counters;             // [2*(round&1)] items, [2*(round&1)+1] cands
 };
 
 __device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int F) {
@@ -429,7 +429,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s.key);
         for (int i = tid; i < RT_TW * RT_TH / 2; i += RT_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
     }
-    if (tid < 2) s.counters[tid] = 0;
+    if (tid < 4) s.counters[tid] = 0;
     __syncthreads();
 
     const int cx0 = max(tx0, vw.xlo), cx1 = min(tx1, vw.xhi);
@@ -437,8 +437,12 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const bool tile_live = cx0 <= cx1 && cy0 <= cy1;
     const int n_rounds = (F + 2 * RT_THREADS - 1) / (2 * RT_THREADS);
     const int chunk = (F + n_rounds - 1) / n_rounds;
+    // Barriers per round: A | sync | B | sync | C, and C runs in the same interval as the next
+    // round's A (they touch disjoint lists); the list counters are double-buffered by round parity.
     for (int round = 0; round < n_rounds && tile_live; ++round) {
         const int f_lo = round * chunk, f_hi = min(F, f_lo + chunk);
+        int* cnt_items = &s.counters[2 * (round & 1)];
+        int* cnt_cands = cnt_items + 1;
         // ---------------- phase A: faces -> row-segment items ----------------
         for (int fb = f_lo + (tid & ~31); fb < f_hi; fb += RT_THREADS) {
             const int f = fb + lane;
@@ -470,7 +474,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             int total;
             const int excl = warp_excl_scan(n, lane, &total);
             int base = 0;
-            if (lane == 0 && total > 0) base = atomicAdd(&s.counters[0], total);
+            if (lane == 0 && total > 0) base = atomicAdd(cnt_items, total);
             base = __shfl_sync(0xffffffffu, base, 0);
             int slot = base + excl;
             for (int j = ja; j <= jb && n > 0; ++j) {
@@ -492,7 +496,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         }
         __syncthreads();
         // ---------------- phase B: items -> candidates ----------------
-        const int n_items = min(s.counters[0], RT_CAP);
+        const int n_items = min(*cnt_items, RT_CAP);
+        if (tid < 2) s.counters[2 * ((round + 1) & 1) + tid] = 0;   // next round's counters (idle since round-1)
         for (int ib0 = tid & ~31; ib0 < n_items; ib0 += RT_THREADS) {
             const int it = ib0 + lane;
             unsigned int hits = 0, f = 0;
@@ -507,7 +512,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             int total;
             const int excl = warp_excl_scan(__popc(hits), lane, &total);
             int base = 0;
-            if (lane == 0 && total > 0) base = atomicAdd(&s.counters[1], total);
+            if (lane == 0 && total > 0) base = atomicAdd(cnt_cands, total);
             base = __shfl_sync(0xffffffffu, base, 0);
             int slot = base + excl;
             while (hits) {
@@ -522,15 +527,13 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         }
         __syncthreads();
         // ---------------- phase C: candidates -> z-buffer ----------------
-        const int n_cands = min(s.counters[1], RT_CAP);
+        const int n_cands = min(*cnt_cands, RT_CAP);
         for (int c = tid; c < n_cands; c += RT_THREADS) {
             const unsigned int e = s.cands[c];
             eval_and_commit(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0);
         }
-        __syncthreads();
-        if (tid < 2) s.counters[tid] = 0;
-        __syncthreads();
     }
+    __syncthreads();
 
     // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299); with a target image the
     // m2d loss partial sums of this tile (train_render.py:728-731) are produced on the way out
