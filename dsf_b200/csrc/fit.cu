@@ -9,15 +9,24 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
 int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale,
                            const float* verts, const float* joints, const float* g_verts,
                            const float* g_joints, const DsfManoGrads* g, float* ws, cudaStream_t st);
+struct CropParams {
+    const float* joints;
+    const float* M;
+    int nj;
+    float fx, fy, px, py;
+    float off_xy, off_z, thick;
+};
 int dsf_raster_tiles(int R);
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
-                            const float* target, float thr, float* parts_tile, cudaStream_t st);
+                            const float* target, float thr, float* parts_tile, const CropParams* crop,
+                            cudaStream_t st);
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
-                             const float* img, const float* parts, float gscale, float thr, cudaStream_t st);
+                             const float* img, const float* parts, float gscale, float thr, const CropParams* crop,
+                             cudaStream_t st);
 int dsf_fold_loss_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
                        cudaStream_t st);
 
@@ -27,7 +36,8 @@ extern "C" long dsf_fit_workspace_floats(int batch, int R) {
 
 extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
                             const float* cube, const float* view, const float* xs, const float* ys,
-                            const float* target, float loss_weight, float* img, int* pix_to_face,
+                            const float* target, float loss_weight, const float* crop_joints, int n_crop_joints,
+                            const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                             float* verts, float* joints, float* g_params, float* parts, float* totals,
                             float* workspace, dsfStream_t stream) {
     dsf_reset_launch_count();
@@ -41,6 +51,11 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     float* parts_tile = workspace + (size_t)batch * WS_PER_HAND;
     float* g_verts = parts_tile + (size_t)batch * n_tiles * 2;
     const float thr = 0.99f;
+    DSF_REQUIRE(!crop_joints || (crop_M && intr4 && n_crop_joints > 0), "crop_joints needs crop_M, intr4 and a joint count");
+    // crop_hand defaults of data/render_loader.py:1209 (offsetxy=25, offsetz=20, hand_thickness=20)
+    CropParams crop = {crop_joints, crop_M, n_crop_joints, 0.f, 0.f, 0.f, 0.f, 25.f, 20.f, 20.f};
+    if (crop_joints) { crop.fx = intr4[0]; crop.fy = intr4[1]; crop.px = intr4[2]; crop.py = intr4[3]; }
+    const CropParams* cropp = crop_joints ? &crop : nullptr;
 
     // params (B,62) = [quat3 | theta45 | beta10 | scale, trans3]   (mano_layer.py:1073-1076)
     DsfManoParams p;
@@ -59,13 +74,13 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     if (rc) return rc;
     // rasterise + normalise; the m2d loss partial sums fall out of the epilogue (no extra pass)
     rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr,
-                                 nullptr, nullptr, target, thr, parts_tile, st);
+                                 nullptr, nullptr, target, thr, parts_tile, cropp, st);
     if (rc) return rc;
     rc = dsf_fold_loss_impl(batch, n_tiles, loss_weight, parts_tile, parts, totals, st);
     if (rc) return rc;
     // backward recomputes d loss / d img per pixel from (target, img, N_b): no gradient image in HBM
     rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, nullptr,
-                                  g_verts, target, img, parts, loss_weight / (float)batch, thr, st);
+                                  g_verts, target, img, parts, loss_weight / (float)batch, thr, cropp, st);
     if (rc) return rc;
     rc = dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
     return rc;

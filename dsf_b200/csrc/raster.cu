@@ -249,6 +249,96 @@ __device__ __forceinline__ float seg_dist_rn(float px, float py, float ax, float
 }
 
 // ------------------------------------------------------------------------------------------------
+// crop_hand ("next" row f1): keep only pixels whose back-projected 3-D point lies inside the box
+// around the teacher skeleton - data/render_loader.py:1209-1227 with uvdImg2xyzImg (:1190-1200),
+// uvd_nl2xyz_tensor (:1044-1057) and pointsImgTo3D (:336-343, flip = 1).
+// ------------------------------------------------------------------------------------------------
+struct CropParams {
+    const float* joints;   // (B, nj, 3) normalised teacher joints, or nullptr = no crop
+    const float* M;        // (B,3,3) axis-aligned crop transform
+    int nj;
+    float fx, fy, px, py;
+    float off_xy, off_z, thick;
+};
+
+struct CropBox {
+    float lo[3], hi[3];
+    float s_x, t_x, s_y, t_y;
+};
+
+// one warp: box = skeleton bounds +- offsets (skeleton = joint * cube / 2 + centre)
+__device__ __forceinline__ void crop_box_warp(const CropParams& cp, int mesh, const float* center, const float* cube,
+                                              int lane, CropBox* out) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = lane; j < cp.nj; j += 32) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fadd_rn(__fdiv_rn(__fmul_rn(cp.joints[((size_t)mesh * cp.nj + j) * 3 + c], cube[3 * mesh + c]), 2.f),
+                                      center[3 * mesh + c]);
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    if (lane == 0) {
+        out->lo[0] = lo[0] - cp.off_xy; out->hi[0] = hi[0] + cp.off_xy;
+        out->lo[1] = lo[1] - cp.off_xy; out->hi[1] = hi[1] + cp.off_xy;
+        out->lo[2] = lo[2] - cp.off_z - cp.thick; out->hi[2] = hi[2] + cp.off_z;
+        const float* m = cp.M + 9 * (size_t)mesh;
+        out->s_x = m[0]; out->t_x = m[2]; out->s_y = m[4]; out->t_y = m[5];
+    }
+}
+
+// does crop_hand keep pixel (row, col) of an R x R normalised depth image with value val?
+__device__ __forceinline__ bool crop_keep(const CropBox& b, const CropParams& cp, int row, int col, int R, float val,
+                                          float zc, float zh) {
+    const float rm1 = (float)R - 1.f, half = (float)R * 0.5f;
+    const float gu = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, (float)col), rm1), 1.f);
+    const float gv = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, (float)row), rm1), 1.f);
+    const float uu = __fmul_rn(__fadd_rn(gu, 1.f), half), vv = __fmul_rn(__fadd_rn(gv, 1.f), half);
+    const float d = __fadd_rn(__fmul_rn(val, zh), zc);
+    const float us = __fdiv_rn(__fsub_rn(uu, b.t_x), b.s_x), vs = __fdiv_rn(__fsub_rn(vv, b.t_y), b.s_y);
+    const float x = __fdiv_rn(__fmul_rn(__fsub_rn(us, cp.px), d), cp.fx);
+    const float y = __fdiv_rn(__fmul_rn(__fsub_rn(vs, cp.py), d), cp.fy);
+    return x > b.lo[0] && x < b.hi[0] && y > b.lo[1] && y < b.hi[1] && d > b.lo[2] && d < b.hi[2];
+}
+
+__global__ void __launch_bounds__(256)
+crop_hand_kernel(int R, CropParams cp, const float* __restrict__ center, const float* __restrict__ cube,
+                 const float* __restrict__ img, float* __restrict__ out, unsigned char* __restrict__ keep) {
+    __shared__ CropBox box;
+    const int b = blockIdx.x;
+    if (threadIdx.x < 32) crop_box_warp(cp, b, center, cube, threadIdx.x, &box);
+    __syncthreads();
+    const float zc = center[3 * b + 2], zh = __fdiv_rn(cube[3 * b + 2], 2.f);
+    for (int k = threadIdx.x; k < R * R; k += 256) {
+        const float v = img[(size_t)b * R * R + k];
+        const bool m = crop_keep(box, cp, k / R, k % R, R, v, zc, zh);
+        out[(size_t)b * R * R + k] = m ? v : 1.f;
+        if (keep) keep[(size_t)b * R * R + k] = m ? 1 : 0;
+    }
+}
+
+extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* joints, int n_joints,
+                             const float* center3d, const float* cube, const float* M, const float* intr4,
+                             float offset_xy, float offset_z, float thickness, float* out, unsigned char* keep,
+                             dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && R > 1 && img && joints && n_joints > 0 && center3d && cube && M && intr4 && out,
+                "null / empty argument");
+    CropParams cp = {joints, M, n_joints, intr4[0], intr4[1], intr4[2], intr4[3], offset_xy, offset_z, thickness};
+    crop_hand_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(R, cp, center3d, cube, img, out, keep);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward: grid (tiles, meshes); one CTA owns a 128 x 64 pixel tile of one mesh (half the image at
 // R = 128) with its z-buffer in shared memory as packed 64-bit (depth bits << 32 | face) keys.
 // Work is re-balanced twice through shared-memory lists so that lanes stay busy:
@@ -362,7 +452,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
-                  float thr, float* __restrict__ parts_tile, int use_tma) {
+                  float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RasterSmem s = carve_smem(smem_raw, R, F);
     const int mesh = blockIdx.y;
@@ -540,6 +630,14 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const float zmax = __fadd_rn(vw.zc, vw.zh), zmin_c = __fsub_rn(vw.zc, vw.zh);
     const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
     float l_sum = 0.f, l_cnt = 0.f;
+    // optional crop_hand of the rendered image before the loss (train_render.py:727): the stored
+    // image stays uncropped, only the loss (and its gradient, in the backward kernel) sees the crop
+    CropBox* cbox = reinterpret_cast<CropBox*>(s.cands);
+    const bool do_crop = target && crop.joints;
+    if (do_crop) {
+        if (tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
+        __syncthreads();
+    }
     for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
         for (int lx = lane; lx < tw; lx += 32) {
             const unsigned long long key = s.key[ly * RT_TW + lx];
@@ -555,7 +653,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             p2f[o] = f;
             if (target) {
                 const float t = target[o];
-                if (t < thr || val < thr) { l_sum += fabsf(t - val); l_cnt += 1.f; }
+                const float vc = (do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx, R, val, vw.zc, vw.zh)) ? 1.f : val;
+                if (t < thr || vc < thr) { l_sum += fabsf(t - vc); l_cnt += 1.f; }
             }
             if (zbuf) zbuf[o] = z;
             if (bary || dists) {
@@ -605,7 +704,8 @@ int dsf_raster_tiles(int R) { return ((R + RT_TW - 1) / RT_TW) * ((R + RT_TH - 1
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
-                            const float* target, float thr, float* parts_tile, cudaStream_t st) {
+                            const float* target, float thr, float* parts_tile, const CropParams* crop,
+                            cudaStream_t st) {
     if (h->n_faces > RT_MAXF) {
         dsf_set_error("rasteriser supports at most %d faces (got %d)", RT_MAXF, h->n_faces);
         return DSF_ERR_UNSUPPORTED;
@@ -626,7 +726,8 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
     dim3 grid(tiles_x * tiles_y, n_mesh);
     raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
                                                       h->faces_packed, h->n_faces, view, xs, ys, img, p2f,
-                                                      zbuf, bary, dists, target, thr, parts_tile, use_tma);
+                                                      zbuf, bary, dists, target, thr, parts_tile, use_tma,
+                                                      crop ? *crop : CropParams{});
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -639,7 +740,7 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
     DSF_REQUIRE(n_mesh > 0 && n_mesh <= 65535, "n_mesh must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face,
-                                   zbuf, bary, dists, nullptr, 0.f, nullptr, (cudaStream_t)stream);
+                                   zbuf, bary, dists, nullptr, 0.f, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -658,7 +759,7 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   const int* __restrict__ p2f, const float* __restrict__ g_img, float* __restrict__ g_verts,
                   const float* __restrict__ target, const float* __restrict__ img,
-                  const float* __restrict__ parts, float gscale, float thr) {
+                  const float* __restrict__ parts, float gscale, float thr, CropParams crop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* svn = reinterpret_cast<float*>(smem_raw);
     float* sgn = svn + NVW * 3;
@@ -691,9 +792,15 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     const float* tg = target ? target + (size_t)mesh * R * R : nullptr;
     const float* im = img ? img + (size_t)mesh * R * R : nullptr;
     const float gk = parts ? gscale / (parts[2 * mesh + 1] + 1e-8f) : 0.f;
+    __shared__ CropBox cbox;
+    const bool do_crop = !gi && crop.joints;
+    if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, &cbox);
+    if (do_crop) __syncthreads();
     auto cotangent = [&](int k) -> float {
         if (gi) return gi[k];
         const float a = tg[k], c = im[k];
+        // cropped-away pixels enter the loss as constant background: no gradient
+        if (do_crop && !crop_keep(cbox, crop, k / R, k % R, R, c, vw.zc, vw.zh)) return 0.f;
         if (!(a < thr || c < thr)) return 0.f;
         const float d = c - a;
         return d > 0.f ? gk : (d < 0.f ? -gk : 0.f);
@@ -820,7 +927,8 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
-                             const float* img, const float* parts, float gscale, float thr, cudaStream_t st) {
+                             const float* img, const float* parts, float gscale, float thr, const CropParams* crop,
+                             cudaStream_t st) {
     const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK * 2;
     const int max_smem = (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK * 2);
     static bool attr_set[16] = {};
@@ -833,10 +941,12 @@ int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, c
     }
     if (n_mesh < 2048)
         raster_bwd_kernel<512><<<n_mesh, 512, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
-                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr);
+                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr,
+                                                          crop ? *crop : CropParams{});
     else
         raster_bwd_kernel<256><<<n_mesh, 256, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
-                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr);
+                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr,
+                                                          crop ? *crop : CropParams{});
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -849,7 +959,8 @@ extern "C" int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* ve
     DSF_REQUIRE(n_mesh > 0, "n_mesh must be positive");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_backward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face,
-                                    g_img, g_verts_cam, nullptr, nullptr, nullptr, 0.f, 0.f, (cudaStream_t)stream);
+                                    g_img, g_verts_cam, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr,
+                                    (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -41,6 +41,7 @@ class FitStep:
         self.parts = f(B, 2)
         self.totals = f(4)
         self.ws = f(self.lib.dsf_fit_workspace_floats(B, R))
+        self.crop_joints = None          # (B,J,3) teacher joints -> crop_hand before the loss
         self.use_graph = use_graph
         self._graph = None
         self.launches_per_step = 0
@@ -53,6 +54,14 @@ class FitStep:
         if target is not None:
             self.target.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
 
+    def set_crop_joints(self, joints):
+        """Teacher joints (B,J,3) in normalised cube units: the rendered image is passed through
+        crop_hand (data/render_loader.py:1209) before the m2d loss, as train_render.py:727 does.
+        Call before the first step (the pointer is baked into the captured graph)."""
+        if self._graph is not None:
+            raise RuntimeError("set_crop_joints must be called before the CUDA graph is captured")
+        self.crop_joints = L.f32c(joints).clone()
+
     def _enqueue(self):
         s = L.stream_ptr()
         n = 0
@@ -63,7 +72,9 @@ class FitStep:
         L.check(self.lib.dsf_fit_step(self.layer._handle, self.B, self.R, self.params.data_ptr(),
                                       self.center3d.data_ptr(), self.cube.data_ptr(), self.view.data_ptr(),
                                       self.xs.data_ptr(), self.ys.data_ptr(), self.target.data_ptr(),
-                                      self.loss_weight, self.img.data_ptr(), self.p2f.data_ptr(),
+                                      self.loss_weight, L.ptr(self.crop_joints),
+                                      0 if self.crop_joints is None else self.crop_joints.shape[1],
+                                      self.M.data_ptr(), self._intr, self.img.data_ptr(), self.p2f.data_ptr(),
                                       self.verts.data_ptr(), self.joints.data_ptr(), self.g_params.data_ptr(),
                                       self.parts.data_ptr(), self.totals.data_ptr(), self.ws.data_ptr(), s))
         n += self.lib.dsf_last_launch_count()

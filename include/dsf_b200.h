@@ -159,14 +159,26 @@ const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces);
  * Fused fitting step: M1+M4 -> R1/R4 -> L2 -> R2 -> MANO backward, one call, fixed launch
  * sequence (graph-capturable).  params (B,62) = [quat3|theta45|beta10|scale|trans3]; target
  * (B,R,R) normalised depth; view/xs/ys from dsf_view_setup; cube (B,3), center3d (B,3).
+ * crop_joints (B,n,3) or NULL: teacher joints for crop_hand of the rendered image before the loss.
  * Outputs: img (B,R,R), pix_to_face (B,R,R), verts (B,779,3), joints (B,21,3) (normalised cube
  * units, global_scale 1/125), g_params (B,62) = d loss/d params, parts (B,2), totals (4). */
 long dsf_fit_workspace_floats(int batch, int R);
 int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
                  const float* cube, const float* view, const float* xs, const float* ys,
-                 const float* target, float loss_weight, float* img, int* pix_to_face,
+                 const float* target, float loss_weight, const float* crop_joints, int n_crop_joints,
+                 const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
                  float* workspace, dsfStream_t stream);
+
+/* "next" row f1 - replaces loader.crop_hand (data/render_loader.py:1209-1227, with uvdImg2xyzImg
+ * :1190-1200): pixels whose back-projected point falls outside the box around the teacher skeleton
+ * (joints (B,nj,3) normalised; offsets in mm, reference defaults 25/20/20) become background 1.0.
+ * keep (B,R,R) uint8 mask optional.  The same crop can be applied inside dsf_fit_step to the
+ * rendered image before the loss (crop_joints != NULL), as train_render.py:727 does. */
+int dsf_crop_hand(int batch, int R, const float* img, const float* joints, int n_joints,
+                  const float* center3d, const float* cube, const float* M, const float* intr4,
+                  float offset_xy, float offset_z, float thickness, float* out, unsigned char* keep,
+                  dsfStream_t stream);
 
 /* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
 int dsf_last_launch_count(void);

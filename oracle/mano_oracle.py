@@ -275,3 +275,34 @@ def literal_sample_maps(M, W, H, S, crop):
         q[oob] = -1
         out += [q, (tie | tie2) & ~oob]
     return out[0], out[2], out[1], out[3]
+
+
+# ----------------------------------------------------------------------------------------
+# "next" row f1: crop_hand (data/render_loader.py:1209-1227) with uvdImg2xyzImg (:1190-1200),
+# uvd_nl2xyz_tensor (:1044-1057), get_trans_points (:1113-1118), pointsImgTo3D (:336-343, flip=1)
+# ----------------------------------------------------------------------------------------
+def crop_hand_box(joint, center, cube, offsetxy=25.0, offsetz=20.0, hand_thickness=20.0):
+    """(B,J,3) normalised teacher joints -> (B,6) [minx,maxx,miny,maxy,minz,maxz] in camera mm."""
+    sk = joint * cube[:, None] / 2 + center[:, None]
+    lo, hi = sk.min(1)[0], sk.max(1)[0]
+    return torch.stack([lo[:, 0] - offsetxy, hi[:, 0] + offsetxy, lo[:, 1] - offsetxy, hi[:, 1] + offsetxy,
+                        lo[:, 2] - offsetz - hand_thickness, hi[:, 2] + offsetz], 1)
+
+
+def crop_hand(img, joint, center, M, cube, intr, offsetxy=25.0, offsetz=20.0, hand_thickness=20.0):
+    """img (B,1,R,R) normalised depth -> same with everything outside the skeleton's 3-D box set
+    to background (1.0).  M is the axis-aligned crop transform (its inverse is applied in closed form)."""
+    B, _, R, _ = img.shape
+    fx, fy, px, py = intr
+    box = crop_hand_box(joint, center, cube, offsetxy, offsetz, hand_thickness)
+    g = 2.0 * torch.arange(R, dtype=img.dtype) / (R - 1.0) - 1.0
+    uu = ((g + 1) * (R / 2)).view(1, 1, R)              # column coordinate, crop pixels
+    vv = ((g + 1) * (R / 2)).view(1, R, 1)
+    d = img[:, 0] * (cube[:, 2] / 2.0).view(B, 1, 1) + center[:, 2].view(B, 1, 1)
+    us = (uu - M[:, 0, 2].view(B, 1, 1)) / M[:, 0, 0].view(B, 1, 1)
+    vs = (vv - M[:, 1, 2].view(B, 1, 1)) / M[:, 1, 1].view(B, 1, 1)
+    x = (us - px) * d / fx
+    y = (vs - py) * d / fy
+    b = box.view(B, 6, 1, 1)
+    mask = (x > b[:, 0]) & (x < b[:, 1]) & (y > b[:, 2]) & (y < b[:, 3]) & (d > b[:, 4]) & (d < b[:, 5])
+    return torch.where(mask[:, None], img, torch.ones_like(img)), mask

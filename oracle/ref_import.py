@@ -85,3 +85,39 @@ def make_reference_render(mod, mano_layer, cam_para, image_size, crop_size=(128,
     padd = np.ones([crop_size[0], crop_size[0]])
     r.crop_mesh = torch.from_numpy(np.stack((xx, yy, padd), axis=-1).reshape([1, -1, 3])).float()
     return r
+
+
+def import_reference_loader_module():
+    """data/render_loader.py (for crop_hand / uvdImg2xyzImg): additionally needs matplotlib, PIL,
+    tensorboardX, ... at import time only; permissive stand-ins are registered for whatever is missing."""
+    import_reference_mano_module()
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return _Dummy()
+
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return _Dummy()
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return _Dummy
+
+    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "mpl_toolkits",
+                 "mpl_toolkits.mplot3d", "mpl_toolkits.mplot3d.art3d", "PIL", "PIL.Image", "tensorboardX",
+                 "prefetch_generator", "trimesh", "aabbtree"]:
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = _Any(name)
+    import importlib
+
+    return importlib.import_module("data.render_loader")

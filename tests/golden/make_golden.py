@@ -82,6 +82,22 @@ def main():
     zimg = zimg + (center3d[:, 2] - 800.0).view(B, 1, 1, 1) * (zimg > 0)
     znorm = rnd.normalize_img(zimg.clone(), center2d, cube)
 
+    # crop_hand of the data loader (data/render_loader.py:1209-1227), run on the reference's own class
+    from oracle.ref_import import import_reference_loader_module
+    from oracle import raster_oracle as ro
+    from oracle import mano_oracle as mo
+    rl = import_reference_loader_module()
+    ld = rl.loader.__new__(rl.loader)
+    ld.img_size, ld.paras, ld.flip = 128, NYU, 1
+    consts = mo.ManoConstants(__import__("dsf_b200").make_synthetic_mano(0))
+    vw = verts.detach() * cube[:, None] / 2 + center3d[:, None]
+    view, xs_, ys_, M_d = ro.make_view("direct", center3d, cube, NYU, 640, 480, 128)
+    _, zb, _, _ = ro.render(vw, consts.faces, view, xs_, ys_)
+    crop_in = ro.normalize_depth(zb, view)[:, None]
+    teacher = joints.detach() + 0.05 * torch.randn(joints.shape, generator=torch.Generator().manual_seed(9))
+    teacher[:, :, 2] *= 0.6                                  # a tighter z box so the crop actually bites
+    crop_out = ld.crop_hand(crop_in.clone(), teacher, center3d, M_d, cube)
+
     out = os.path.join(ROOT, "tests", "golden", "mano_golden.npz")
     np.savez_compressed(
         out,
@@ -96,7 +112,9 @@ def main():
         center3d=center3d.numpy(), cube=cube.numpy(), center2d=center2d.numpy(),
         bounds=torch.stack([xs, xe, ys, ye], 1).numpy(), M=M.numpy(), joint_uvd=joint_uvd.detach().numpy(),
         literal_src=src.numpy().astype(np.int32), zimg=zimg.numpy(), znorm=znorm.numpy(),
+        crop_in=crop_in.numpy(), crop_teacher=teacher.numpy(), crop_M=M_d.numpy(), crop_out=crop_out.numpy(),
     )
+    print("crop_hand removed px:", int(((crop_in < 0.99) & (crop_out >= 0.99)).sum()), "of", int((crop_in < 0.99).sum()))
     print("wrote", out, os.path.getsize(out), "bytes")
     print("coll", float(coll), "per hand", coll_per_hand.detach().numpy())
     print("mask ones", int(ref.mask.sum()), "sym", bool((ref.mask == ref.mask.T).all()))
