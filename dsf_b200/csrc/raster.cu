@@ -351,7 +351,9 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 #define RT_TH 64             // tile height: 64 KB of keys -> two CTAs per SM
 #define RT_THREADS 512
 #define RT_MAXR 512
-#define RT_CAP 4096          // entries per list
+#define RT_CAP 4096          // (items + candidates) / 2: list storage in 32-bit entries
+#define RT_WITEMS 128        // per-warp item list      (16 warps x 128 = 2048 entries)
+#define RT_WCANDS 384        // per-warp candidate list (16 warps x 384 = 6144 entries)
 #define RT_SEG 8
 #define RT_MAXF 2047         // face id is packed into 11 bits
 
@@ -361,9 +363,9 @@ struct RasterSmem {
     float* xs;                 // R
     float* ys;                 // R
     unsigned int* fp;          // F packed vertex ids
-    unsigned int* items;       // RT_CAP
-    unsigned int* cands;       // RT_CAP
-    int* counters;             // [2*(round&1)] items, [2*(round&1)+1] cands
+    unsigned int* items;       // per-warp item lists
+    unsigned int* cands;       // per-warp candidate lists
+    int* counters;             // [0] next face batch
 };
 
 __device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int F) {
@@ -374,8 +376,8 @@ __device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int 
     s.ys = s.xs + R;
     s.fp = reinterpret_cast<unsigned int*>(s.ys + R);
     s.items = s.fp + ((F + 3) & ~3);
-    s.cands = s.items + RT_CAP;
-    s.counters = reinterpret_cast<int*>(s.cands + RT_CAP);
+    s.cands = s.items + (RT_THREADS / 32) * RT_WITEMS;
+    s.counters = reinterpret_cast<int*>(s.items + 2 * RT_CAP);
     return s;
 }
 
@@ -468,7 +470,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     if (use_tma) {
         // Stage this mesh's inputs with the TMA engine (cp.async.bulk, SASS UBLKCP): sample grids,
         // packed triangle list and the raw vertex block (16-byte aligned window around the 9348-byte
-        // row, landed in the not-yet-used item list) - one thread issues, an mbarrier collects the bytes.
+        // row, landed in the not-yet-used candidate lists) - one thread issues, an mbarrier collects the bytes.
         __shared__ __align__(8) unsigned long long tma_bar;
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
         const size_t v_off = (size_t)mesh * NVW * 3 * sizeof(float);
@@ -495,7 +497,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                          "l"(faces_packed), "r"(f_bytes), "r"(bar)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(s.items)),
+                             (uint32_t)__cvta_generic_to_shared(s.cands)),
                          "l"(vsrc), "r"(v_bytes), "r"(bar)
                          : "memory");
         }
@@ -507,7 +509,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         asm volatile(
             "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n" ::"r"(bar)
             : "memory");
-        const float* raw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(s.items) + v_shift);
+        const float* raw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(s.cands) + v_shift);
         for (int v = tid; v < NVW; v += RT_THREADS) project_vertex(raw + 3 * v, ps, po, vw, s.vn + 3 * v);
     } else {
         for (int i = tid; i < R; i += RT_THREADS) {
@@ -525,104 +527,93 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const int cx0 = max(tx0, vw.xlo), cx1 = min(tx1, vw.xhi);
     const int cy0 = max(ty0, vw.ylo), cy1 = min(ty1, vw.yhi);
     const bool tile_live = cx0 <= cx1 && cy0 <= cy1;
-    const int n_rounds = (F + 2 * RT_THREADS - 1) / (2 * RT_THREADS);
-    const int chunk = (F + n_rounds - 1) / n_rounds;
-    // Barriers per round: A | sync | B | sync | C, and C runs in the same interval as the next
-    // round's A (they touch disjoint lists); the list counters are double-buffered by round parity.
-    for (int round = 0; round < n_rounds && tile_live; ++round) {
-        const int f_lo = round * chunk, f_hi = min(F, f_lo + chunk);
-        int* cnt_items = &s.counters[2 * (round & 1)];
-        int* cnt_cands = cnt_items + 1;
-        // ---------------- phase A: faces -> row-segment items ----------------
-        for (int fb = f_lo + (tid & ~31); fb < f_hi; fb += RT_THREADS) {
-            const int f = fb + lane;
-            int ia = 0, ib = -1, ja = 0, jb = -1;
-            if (f < f_hi) {
-                const unsigned int pk = s.fp[f];
-                const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
-                const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1], z0 = s.vn[3 * a0 + 2];
-                const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1], z1 = s.vn[3 * a1 + 2];
-                const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
-                const float zmin = fminf(z0, fminf(z1, z2));
-                const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
-                // behind / at the camera, or degenerate in NDC
-                if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
-                    const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
-                    const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
-                    // rows first: tiles split the image in y, so half the faces drop out here
-                    ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
-                    jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
-                    if (ja <= jb) {
-                        ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
-                        ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
-                    }
-                }
-            }
-            const int w = ib - ia + 1, hgt = jb - ja + 1;
-            const int nseg = (w + RT_SEG - 1) / RT_SEG;
-            const int n = (w > 0 && hgt > 0) ? nseg * hgt : 0;
-            int total;
-            const int excl = warp_excl_scan(n, lane, &total);
-            int base = 0;
-            if (lane == 0 && total > 0) base = atomicAdd(cnt_items, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            int slot = base + excl;
-            for (int j = ja; j <= jb && n > 0; ++j) {
-                for (int i0 = ia; i0 <= ib; i0 += RT_SEG, ++slot) {
-                    const int len = min(RT_SEG, ib - i0 + 1);
-                    if (slot < RT_CAP) {
-                        s.items[slot] = (unsigned int)f | ((unsigned int)(j - ty0) << 11) |
-                                        ((unsigned int)(i0 - tx0) << 18) | ((unsigned int)(len - 1) << 25);
-                    } else {                                     // list full: evaluate in place
-                        unsigned int hits = segment_hits(s, f, i0, len, j);
-                        while (hits) {
-                            const int k = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            eval_and_commit(s, f, i0 + k, j, tx0, ty0);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---------------- phase B: items -> candidates ----------------
-        const int n_items = min(*cnt_items, RT_CAP);
-        if (tid < 2) s.counters[2 * ((round + 1) & 1) + tid] = 0;   // next round's counters (idle since round-1)
-        for (int ib0 = tid & ~31; ib0 < n_items; ib0 += RT_THREADS) {
-            const int it = ib0 + lane;
-            unsigned int hits = 0, f = 0;
-            int i0 = 0, j = 0;
-            if (it < n_items) {
-                const unsigned int e = s.items[it];
-                f = e & 2047u;
-                j = ty0 + (int)((e >> 11) & 127u);
-                i0 = tx0 + (int)((e >> 18) & 127u);
-                hits = segment_hits(s, f, i0, (int)((e >> 25) & 7u) + 1, j);
-            }
-            int total;
-            const int excl = warp_excl_scan(__popc(hits), lane, &total);
-            int base = 0;
-            if (lane == 0 && total > 0) base = atomicAdd(cnt_cands, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            int slot = base + excl;
-            while (hits) {
-                const int k = __ffs(hits) - 1;
-                hits &= hits - 1;
-                if (slot < RT_CAP)
-                    s.cands[slot] = f | ((unsigned int)(j - ty0) << 11) | ((unsigned int)(i0 + k - tx0) << 18);
-                else
-                    eval_and_commit(s, f, i0 + k, j, tx0, ty0);
-                ++slot;
-            }
-        }
-        __syncthreads();
-        // ---------------- phase C: candidates -> z-buffer ----------------
-        const int n_cands = min(*cnt_cands, RT_CAP);
-        for (int c = tid; c < n_cands; c += RT_THREADS) {
-            const unsigned int e = s.cands[c];
+    // Each warp pulls batches of 32 faces from a shared counter and runs the three phases on its
+    // own private lists (warp-level synchronisation only), so no CTA barrier separates the phases
+    // and a slow batch never stalls the other warps; the z-buffer is shared through atomicMin.
+    const int warp = tid >> 5;
+    unsigned int* my_items = s.items + warp * RT_WITEMS;
+    unsigned int* my_cands = s.cands + warp * RT_WCANDS;
+    int n_cands = 0;
+    auto flush_cands = [&]() {
+        __syncwarp();                                         // candidate writes of all lanes visible
+        for (int c = lane; c < n_cands; c += 32) {
+            const unsigned int e = my_cands[c];
             eval_and_commit(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0);
         }
+        n_cands = 0;
+        __syncwarp();
+    };
+    while (tile_live) {
+        int fb = 0;
+        if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
+        fb = __shfl_sync(0xffffffffu, fb, 0);
+        if (fb >= F) break;
+        // ---------------- phase A: 32 faces -> row-segment items ----------------
+        const int f = fb + lane;
+        int ia = 0, ib = -1, ja = 0, jb = -1;
+        if (f < F) {
+            const unsigned int pk = s.fp[f];
+            const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+            const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1], z0 = s.vn[3 * a0 + 2];
+            const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1], z1 = s.vn[3 * a1 + 2];
+            const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
+            const float zmin = fminf(z0, fminf(z1, z2));
+            const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
+            // behind / at the camera, or degenerate in NDC
+            if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
+                const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
+                const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
+                // rows first: tiles split the image in y, so half the faces drop out here
+                ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
+                jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
+                if (ja <= jb) {
+                    ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
+                    ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
+                }
+            }
+        }
+        const int w = ib - ia + 1, hgt = jb - ja + 1;
+        const int nseg = (w + RT_SEG - 1) / RT_SEG;
+        const int n = (w > 0 && hgt > 0) ? nseg * hgt : 0;
+        int total;
+        const int excl = warp_excl_scan(n, lane, &total);
+        for (int w0 = 0; w0 < total; w0 += RT_WITEMS) {          // windows of the batch's item sequence
+            const int k_lo = max(0, w0 - excl), k_hi = min(n, w0 + RT_WITEMS - excl);
+            for (int k = k_lo; k < k_hi; ++k) {
+                const int row = nseg == 1 ? k : k / nseg;
+                const int i0 = ia + (k - row * nseg) * RT_SEG;
+                const int len = min(RT_SEG, ib - i0 + 1);
+                my_items[excl + k - w0] = (unsigned int)f | ((unsigned int)(ja + row - ty0) << 11) |
+                                          ((unsigned int)(i0 - tx0) << 18) | ((unsigned int)(len - 1) << 25);
+            }
+            __syncwarp();
+            // ---------------- phase B: items -> candidates ----------------
+            const int n_items = min(RT_WITEMS, total - w0);
+            for (int it0 = 0; it0 < n_items; it0 += 32) {
+                if (n_cands > RT_WCANDS - 32 * RT_SEG) flush_cands();      // phase C when the list may overflow
+                const int it = it0 + lane;
+                unsigned int hits = 0, fi = 0;
+                int i0 = 0, j = 0;
+                if (it < n_items) {
+                    const unsigned int e = my_items[it];
+                    fi = e & 2047u;
+                    j = ty0 + (int)((e >> 11) & 127u);
+                    i0 = tx0 + (int)((e >> 18) & 127u);
+                    hits = segment_hits(s, fi, i0, (int)((e >> 25) & 7u) + 1, j);
+                }
+                int c_total;
+                int slot = n_cands + warp_excl_scan(__popc(hits), lane, &c_total);
+                while (hits) {
+                    const int k = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    my_cands[slot++] = fi | ((unsigned int)(j - ty0) << 11) | ((unsigned int)(i0 + k - tx0) << 18);
+                }
+                n_cands += c_total;
+            }
+            __syncwarp();
+        }
     }
+    flush_cands();                                            // ---------------- phase C (remainder)
     __syncthreads();
 
     // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299); with a target image the
