@@ -55,6 +55,7 @@ struct DsfMano {
     float* wj_w;
     int* faces;    // (n_faces,3)
     unsigned int* faces_packed;   // (n_faces) i0 | i1 << 10 | i2 << 20
+    unsigned short* face_order;   // (n_faces) face ids, largest rest-pose area first
     int n_faces;
     float* coll_mask;  // (66,66)
     int parents[NJ];

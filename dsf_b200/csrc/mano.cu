@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +40,7 @@ static int upload(T** dst, const T* src, size_t n) {
 }
 
 void dsf_build_collision_mask(float* m);   // coll.cu
+static const int h_ring[16] = {121, 214, 215, 279, 239, 234, 92, 38, 122, 118, 117, 119, 120, 108, 79, 78};
 
 extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     DSF_REQUIRE(host && out, "null host/out");
@@ -170,6 +173,29 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
         fpk[f] = (unsigned)host->faces[3 * f] | ((unsigned)host->faces[3 * f + 1] << 10) |
                  ((unsigned)host->faces[3 * f + 2] << 20);
     rc |= upload(&h->faces_packed, fpk.data(), fpk.size());
+    {   // processing order of the rasteriser: largest triangles (rest pose) first
+        std::vector<std::pair<float, int>> area(host->n_faces);
+        auto vtx = [&](int v, int c) {
+            if (v < NV) return host->v_template[3 * v + c];
+            float a = 0.f;                                   // wrist-cap centre = mean of the ring
+            for (int i = 0; i < 16; ++i) a += host->v_template[3 * h_ring[i] + c];
+            return a / 16.f;
+        };
+        for (int f = 0; f < host->n_faces; ++f) {
+            float e1[3], e2[3];
+            for (int c = 0; c < 3; ++c) {
+                e1[c] = vtx(host->faces[3 * f + 1], c) - vtx(host->faces[3 * f], c);
+                e2[c] = vtx(host->faces[3 * f + 2], c) - vtx(host->faces[3 * f], c);
+            }
+            const float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2],
+                        cz = e1[0] * e2[1] - e1[1] * e2[0];
+            area[f] = {-(cx * cx + cy * cy + cz * cz), f};
+        }
+        std::sort(area.begin(), area.end());
+        std::vector<unsigned short> order(host->n_faces);
+        for (int f = 0; f < host->n_faces; ++f) order[f] = (unsigned short)area[f].second;
+        rc |= upload(&h->face_order, order.data(), order.size());
+    }
     rc |= upload(&h->coll_mask, mask.data(), mask.size());
     h->n_faces = host->n_faces;
     if (rc) {
@@ -184,7 +210,7 @@ extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
     void* ptrs[] = {h->BTh, h->BTl, h->Bh, h->Bl, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
                     h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx, h->wj_w, h->faces, h->faces_packed,
-                    h->coll_mask};
+                    h->face_order, h->coll_mask};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free(h);
@@ -330,7 +356,6 @@ int dsf_blend_backward_splits(int M);
 // vertex (:636-637), unit / camera scaling (:662-675).
 // ------------------------------------------------------------------------------------------------
 #define SKIN_T 128
-static const int h_ring[16] = {121, 214, 215, 279, 239, 234, 92, 38, 122, 118, 117, 119, 120, 108, 79, 78};
 static const int h_tips[5] = {333, 444, 672, 555, 744};
 __constant__ int c_ring[16];
 __constant__ int c_tips[5];

@@ -450,7 +450,8 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
 
 __global__ void __launch_bounds__(RT_THREADS, 2)
 raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const float* __restrict__ place_scale,
-                  const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed, int F,
+                  const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed,
+                  const unsigned short* __restrict__ face_order, int F,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
@@ -467,6 +468,14 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const float* vm = verts + (size_t)mesh * NVW * 3;
     const float* ps = place_scale ? place_scale + 3 * mesh : nullptr;
     const float* po = place_off ? place_off + 3 * mesh : nullptr;
+    if (target) {
+        // the target tile is only needed in the epilogue: pull it into L2 now, behind the raster work
+        const int rows = ty1 - ty0 + 1, lines_per_row = ((tx1 - tx0 + 1) * 4 + 127) / 128;
+        for (int i = tid; i < rows * lines_per_row; i += RT_THREADS) {
+            const float* pa = target + ((size_t)mesh * R + ty0 + i / lines_per_row) * R + tx0 + (i % lines_per_row) * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
+    }
     if (use_tma) {
         // Stage this mesh's inputs with the TMA engine (cp.async.bulk, SASS UBLKCP): sample grids,
         // packed triangle list and the raw vertex block (16-byte aligned window around the 9348-byte
@@ -549,7 +558,9 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         fb = __shfl_sync(0xffffffffu, fb, 0);
         if (fb >= F) break;
         // ---------------- phase A: 32 faces -> row-segment items ----------------
-        const int f = fb + lane;
+        // batches follow face_order (largest rest-pose area first) so the expensive batches are
+        // handed out early and the warps drain together before the epilogue barrier
+        const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
         int ia = 0, ib = -1, ja = 0, jb = -1;
         if (f < F) {
             const unsigned int pk = s.fp[f];
@@ -630,7 +641,19 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         __syncthreads();
     }
     for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
-        for (int lx = lane; lx < tw; lx += 32) {
+        // all target loads of the row are issued before any of them is consumed
+        float tg[RT_TW / 32];
+        if (target) {
+#pragma unroll
+            for (int q = 0; q < RT_TW / 32; ++q) {
+                const int lx = lane + 32 * q;
+                tg[q] = lx < tw ? __ldg(target + ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx)) : 1.f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RT_TW / 32; ++q) {
+            const int lx = lane + 32 * q;
+            if (lx >= tw) continue;
             const unsigned long long key = s.key[ly * RT_TW + lx];
             const int f = key == ~0ull ? -1 : (int)(unsigned int)(key & 0xffffffffu);
             const float z = f < 0 ? -1.f : __uint_as_float((unsigned int)(key >> 32));
@@ -643,7 +666,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             img[o] = val;
             p2f[o] = f;
             if (target) {
-                const float t = target[o];
+                const float t = tg[q];
                 const float vc = (do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx, R, val, vw.zc, vw.zh)) ? 1.f : val;
                 if (t < thr || vc < thr) { l_sum += fabsf(t - vc); l_cnt += 1.f; }
             }
@@ -716,7 +739,7 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
                         ((uintptr_t)ys % 16 == 0);
     dim3 grid(tiles_x * tiles_y, n_mesh);
     raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
-                                                      h->faces_packed, h->n_faces, view, xs, ys, img, p2f,
+                                                      h->faces_packed, h->face_order, h->n_faces, view, xs, ys, img, p2f,
                                                       zbuf, bary, dists, target, thr, parts_tile, use_tma,
                                                       crop ? *crop : CropParams{});
     DSF_CHECK_LAUNCH();
