@@ -31,8 +31,9 @@ UNIT = "fits/s"
 CROP = 128
 # algorithmic bytes per hand-fit at R=128, 1 view
 BYTES_PER_FIT = 2 * CROP * CROP * 4 + 779 * 3 * 4 + 21 * 3 * 4 + 62 * 4 + 62 * 4 + 4 + 60   # 141 232
-# the rasteriser kernel alone: reads verts + view/sample grids, writes normalised depth + pix_to_face
-RASTER_BYTES_PER_HAND = 779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 2 * CROP * CROP * 4
+# the rasteriser kernel as launched in the fused step: reads verts + view/sample grids + the target
+# image, writes normalised depth + pix_to_face + per-tile loss partial sums
+RASTER_BYTES_PER_HAND = 779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 3 * CROP * CROP * 4 + 16
 
 
 def measured_peaks():
@@ -176,12 +177,15 @@ def stage_times(step, iters=10):
     gp = step.g_params
     g = L.DsfManoGrads(gp.data_ptr(), 62, gp.data_ptr() + 12, 62, gp.data_ptr() + 192, 62, gp.data_ptr() + 232, 62)
     mws = torch.empty(lib.dsf_mano_workspace_floats(B), device=step.dev)
+    parts_tile = torch.empty(B * lib.dsf_raster_tiles(R) * 2, device=step.dev)
     stages = {
         "mano_forward(3 kernels)": lambda: L.check(lib.dsf_mano_forward(
             h, B, C.byref(p), 8.0, step.verts.data_ptr(), step.joints.data_ptr(), None, mws.data_ptr(), s)),
+        # the rasteriser exactly as the fused step launches it: target in, loss partial sums out
         "raster_fwd_kernel": lambda: L.check(lib.dsf_raster_forward(
             h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
-            step.img.data_ptr(), step.p2f.data_ptr(), None, None, None, s)),
+            step.img.data_ptr(), step.p2f.data_ptr(), None, None, None, step.target.data_ptr(), 0.99,
+            parts_tile.data_ptr(), s)),
         "depth_loss(2 kernels, modular path only)": lambda: L.check(lib.dsf_depth_loss(
             0, B, R, step.target.data_ptr(), step.img.data_ptr(), 0.99, 0.1, step.parts.data_ptr(),
             step.totals.data_ptr(), g_img.data_ptr(), s)),

@@ -60,7 +60,8 @@ SIGNATURES = {
     "dsf_mano_backward": (_I, [_VP, _I, C.POINTER(DsfManoParams), _F, _VP, _VP, _VP, _VP,
                                C.POINTER(DsfManoGrads), _VP, _VP]),
     "dsf_view_setup": (_I, [_I, _I, _VP, _VP, c_float_p, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "dsf_raster_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_raster_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
+    "dsf_raster_tiles": (_I, [_I]),
     "dsf_raster_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "dsf_depth_loss": (_I, [_I, _I, _I, _VP, _VP, _F, _F, _VP, _VP, _VP, _VP]),
     "dsf_coll_forward_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -16,7 +16,7 @@ struct CropParams {
     float fx, fy, px, py;
     float off_xy, off_z, thick;
 };
-int dsf_raster_tiles(int R);
+extern "C" int dsf_raster_tiles(int R);
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,

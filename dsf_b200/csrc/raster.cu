@@ -713,7 +713,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     }
 }
 
-int dsf_raster_tiles(int R) { return ((R + RT_TW - 1) / RT_TW) * ((R + RT_TH - 1) / RT_TH); }
+extern "C" int dsf_raster_tiles(int R) { return ((R + RT_TW - 1) / RT_TW) * ((R + RT_TH - 1) / RT_TH); }
 
 int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                             const float* place_off, const float* view, const float* xs, const float* ys,
@@ -748,13 +748,15 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
 
 extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                                   const float* xs, const float* ys, int R, float* img, int* pix_to_face,
-                                  float* zbuf, float* bary, float* dists, dsfStream_t stream) {
+                                  float* zbuf, float* bary, float* dists, const float* target, float thr,
+                                  float* loss_parts_tile, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && verts_cam && view && xs && ys && img && pix_to_face, "null argument");
+    DSF_REQUIRE(!target == !loss_parts_tile, "target and loss_parts_tile go together");
     DSF_REQUIRE(n_mesh > 0 && n_mesh <= 65535, "n_mesh must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face,
-                                   zbuf, bary, dists, nullptr, 0.f, nullptr, nullptr, (cudaStream_t)stream);
+                                   zbuf, bary, dists, target, thr, loss_parts_tile, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

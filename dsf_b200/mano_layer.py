@@ -120,7 +120,7 @@ class _RasterFunction(torch.autograd.Function):
         p2f = torch.empty(NM, R, R, dtype=torch.int32, device=dev)
         L.check(lib.dsf_raster_forward(layer._handle, NM, verts_cam.data_ptr(), view.data_ptr(), xs.data_ptr(),
                                        ys.data_ptr(), R, img.data_ptr(), p2f.data_ptr(), None, None, None,
-                                       L.stream_ptr()))
+                                       None, 0.0, None, L.stream_ptr()))
         ctx.layer = layer
         ctx.save_for_backward(verts_cam, view, xs, ys, p2f)
         ctx.mark_non_differentiable(p2f)

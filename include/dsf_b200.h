@@ -110,10 +110,15 @@ int dsf_view_setup(int mode, int batch, const float* center3d, const float* cube
  * background fill (:1084-1085) and normalize_img (:1289-1299).
  * verts_cam (NM,779,3) camera-space mm; faces come from the handle.
  * img (NM,R,R) normalised depth; pix_to_face (NM,R,R) int32 (-1 bg, index local to the mesh);
- * optional Fragments outputs zbuf (NM,R,R), bary (NM,R,R,3), dists (NM,R,R) with -1 background. */
+ * optional Fragments outputs zbuf (NM,R,R), bary (NM,R,R,3), dists (NM,R,R) with -1 background.
+ * optional fused m2d loss: with target (NM,R,R) the epilogue also writes, per mesh and tile,
+ * [sum |target - img| * mask, mask count] (union mask at thr) to loss_parts_tile (NM, tiles, 2). */
 int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                        const float* xs, const float* ys, int R, float* img, int* pix_to_face,
-                       float* zbuf, float* bary, float* dists, dsfStream_t stream);
+                       float* zbuf, float* bary, float* dists, const float* target, float thr,
+                       float* loss_parts_tile, dsfStream_t stream);
+/* number of tiles per mesh = length of the per-mesh partial-sum records of loss_parts_tile */
+int dsf_raster_tiles(int R);
 
 /* R2  replaces _C.rasterize_meshes_backward + the index_put to verts + the camera chain, for
  * the zbuf-only gradient DSF uses.  g_img (NM,R,R) is the cotangent of img.
