@@ -341,6 +341,36 @@ def run_ours(args):
             other[name] = {"hands": b2, "ms_per_step": t2, "fits_per_s": b2 / (t2 * 1e-3),
                            "step_hbm_frac": BYTES_PER_FIT * b2 / (t2 * 1e-3) / 1e9 / peak,
                            "note": "inputs fit in L2 at this size (no flush): latency/launch-bound regime"}
+        # config C4 (BASELINE.json configs[4]): self-penetration + point-to-mesh terms, batch 1024
+        from dsf_b200.mesh_loss import _PointFaceDistance
+        b4, P = 1024, 2048
+        i4 = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(b4, seed=5).items()}
+        p4 = i4["params"]
+        v4, j4 = layer.get_mano_vertices(p4[:, :3], p4[:, 3:48], p4[:, 48:58], p4[:, 58:], global_scale=1 / 125)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        idx = torch.randint(0, 778, (b4, P), device=dev, generator=gen)
+        pcl = torch.gather(v4, 1, idx[..., None].expand(-1, -1, 3)) + 0.05 * torch.randn(b4, P, 3, device=dev, generator=gen)
+        vg = v4.detach().requires_grad_(True)
+
+        def icp():
+            d, _ = _PointFaceDistance.apply(pcl, vg, layer.faces_int)
+            d.mean().backward()
+            vg.grad = None
+
+        jg = j4.detach().requires_grad_(True)
+
+        def coll():
+            layer.calculate_coll(jg, v4.detach()).backward()
+            jg.grad = None
+
+        for fn in (icp, coll):
+            fn()
+        t_icp, t_coll = time_region(icp, 5), time_region(coll, 20)
+        pairs = b4 * P * layer.faces_int.shape[0]
+        other["C4_icp_batch1024"] = {"hands": b4, "points": P, "faces": int(layer.faces_int.shape[0]),
+                                     "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
+                                     "note": "brute-force ICPLoss fwd+bwd; FP32 compute bound, bytes negligible"}
+        other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cstep, cores = cpu_pipeline(args.ref_batch)

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdsf_b200.so")
+SO_PATH = os.environ.get("DSF_B200_LIB", os.path.join(_HERE, "libdsf_b200.so"))   # override: kernel-tuning experiments
 
 VIEW_STRIDE = 16
 NV, NVW, NJ, NJOUT, NSPHERE = 778, 779, 16, 21, 66

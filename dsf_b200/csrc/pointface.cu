@@ -9,7 +9,7 @@
 
 #define PF_EPS 1e-8f
 #define PF_THREADS 128
-#define PF_CHUNK 512     // faces staged per pass: 512 * 9 floats = 18 KB
+#define PF_CHUNK 448     // faces staged per pass: 448 records * 96 B = 42 KB of shared memory
 
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
@@ -64,10 +64,46 @@ __device__ __forceinline__ float point_tri(V3 p, V3 v0, V3 v1, V3 v2, int* branc
     return d;
 }
 
+// Per-face record staged in shared memory once per chunk so that the inner (point, face) test is
+// pure multiply-add work: no square root, no division (they are hoisted into the record).
+#define PF_REC 24
+// [0..2] v0  [3..5] e1=v1-v0  [6..8] e2=v2-v0  [9..11] unit normal  [12] d00 [13] d01 [14] d11
+// [15] 1/(d00 d11 - d01^2 + eps)  [16] 1/|e1|^2  [17] 1/|e2|^2  [18] 1/|v2-v1|^2  (0 = degenerate edge)
+// [19] 1 if |n| > eps
+__device__ __forceinline__ void build_face_record(const float* vb, const int* faces, int f, float* r) {
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const V3 v0 = v3(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2]);
+    const V3 v1 = v3(vb[3 * i1], vb[3 * i1 + 1], vb[3 * i1 + 2]);
+    const V3 v2 = v3(vb[3 * i2], vb[3 * i2 + 1], vb[3 * i2 + 2]);
+    const V3 e1 = v1 - v0, e2 = v2 - v0, e12 = v2 - v1;
+    const V3 n = cross(e2, e1);
+    const float nn = sqrtf(dot(n, n));
+    const V3 nh = n * (1.f / (nn + PF_EPS));
+    const float d00 = dot(e1, e1), d01 = dot(e1, e2), d11 = dot(e2, e2), l12 = dot(e12, e12);
+    r[0] = v0.x; r[1] = v0.y; r[2] = v0.z;
+    r[3] = e1.x; r[4] = e1.y; r[5] = e1.z;
+    r[6] = e2.x; r[7] = e2.y; r[8] = e2.z;
+    r[9] = nh.x; r[10] = nh.y; r[11] = nh.z;
+    r[12] = d00; r[13] = d01; r[14] = d11;
+    r[15] = 1.f / (d00 * d11 - d01 * d01 + PF_EPS);
+    r[16] = d00 <= PF_EPS ? 0.f : 1.f / d00;
+    r[17] = d11 <= PF_EPS ? 0.f : 1.f / d11;
+    r[18] = l12 <= PF_EPS ? 0.f : 1.f / l12;
+    r[19] = nn > PF_EPS ? 1.f : 0.f;
+}
+
+// squared distance from the point with offset a = p - origin to the segment origin + t d, t in [0,1];
+// inv_l2 == 0 marks a degenerate segment: distance to its far end (PointLine3DistanceForward)
+__device__ __forceinline__ float seg_d2(V3 a, V3 d, float inv_l2) {
+    float t = inv_l2 == 0.f ? 1.f : fminf(fmaxf(dot(d, a) * inv_l2, 0.f), 1.f);
+    const V3 q = a - d * t;
+    return dot(q, q);
+}
+
 __global__ void __launch_bounds__(PF_THREADS)
 point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, const float* __restrict__ verts,
                       const int* __restrict__ faces, float* __restrict__ dists, int* __restrict__ idxs) {
-    __shared__ float s_tri[PF_CHUNK * 9];
+    __shared__ __align__(16) float s_rec[PF_CHUNK * PF_REC];
     const int b = blockIdx.y;
     const int pi = blockIdx.x * PF_THREADS + threadIdx.x;
     const bool live = pi < P;
@@ -79,15 +115,29 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
     for (int f0 = 0; f0 < F; f0 += PF_CHUNK) {
         const int nf = min(PF_CHUNK, F - f0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nf * 3; i += PF_THREADS) {
-            const int v = faces[3 * f0 + i];
-            s_tri[3 * i] = vb[3 * v]; s_tri[3 * i + 1] = vb[3 * v + 1]; s_tri[3 * i + 2] = vb[3 * v + 2];
-        }
+        for (int i = threadIdx.x; i < nf; i += PF_THREADS) build_face_record(vb, faces, f0 + i, s_rec + i * PF_REC);
         __syncthreads();
         for (int f = 0; f < nf; ++f) {
-            const float* t = s_tri + 9 * f;
-            int br;
-            const float d = point_tri(p, v3(t[0], t[1], t[2]), v3(t[3], t[4], t[5]), v3(t[6], t[7], t[8]), &br);
+            const float4* r4 = reinterpret_cast<const float4*>(s_rec + f * PF_REC);
+            const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+            const V3 v0 = v3(q0.x, q0.y, q0.z), e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
+            const V3 nh = v3(q2.y, q2.z, q2.w);
+            const V3 a = p - v0;                                 // point relative to v0
+            const float t = -dot(a, nh);                         // signed plane distance (v0 - p) . n
+            const V3 c = a + nh * t;                             // projection on the plane, relative to v0
+            const float d20 = dot(c, e1), d21 = dot(c, e2);
+            const float w1 = (q3.z * d20 - q3.y * d21) * q3.w;   // (d11 d20 - d01 d21) / den
+            const float w2 = (q3.x * d21 - q3.y * d20) * q3.w;   // (d00 d21 - d01 d20) / den
+            const float w0 = 1.f - w1 - w2;
+            float d;
+            if (q4.w != 0.f && w0 >= 0.f && w0 <= 1.f && w1 >= 0.f && w1 <= 1.f && w2 >= 0.f && w2 <= 1.f) {
+                d = t * t;
+            } else {
+                const float e01 = seg_d2(a, e1, q4.x);
+                const float e02 = seg_d2(a, e2, q4.y);
+                const float e12 = seg_d2(a - e1, e2 - e1, q4.z);
+                d = fminf(fminf(e01, e02), e12);
+            }
             if (d < best) { best = d; bi = f0 + f; }      // strict: lowest face index wins ties
         }
     }

@@ -352,9 +352,13 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 #define RT_THREADS 512
 #define RT_MAXR 512
 #define RT_CAP 4096          // (items + candidates) / 2: list storage in 32-bit entries
+#ifndef RT_WITEMS
 #define RT_WITEMS 128        // per-warp item list      (16 warps x 128 = 2048 entries)
-#define RT_WCANDS 384        // per-warp candidate list (16 warps x 384 = 6144 entries)
+#endif
+#define RT_WCANDS (512 - RT_WITEMS)   // per-warp candidate list (16 warps x 512 entries in total)
+#ifndef RT_SEG
 #define RT_SEG 8
+#endif
 #define RT_MAXF 2047         // face id is packed into 11 bits
 
 struct RasterSmem {
