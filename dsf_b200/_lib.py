@@ -67,6 +67,10 @@ SIGNATURES = {
     "dsf_coll_forward_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_point_face_forward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_point_face_backward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_sphere_set": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_seg_pcl": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_joint_icp_forward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_joint_icp_backward": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_fit_workspace_floats": (_L, [_I, _I]),
     "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _I, _VP, c_float_p,
                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -63,6 +63,83 @@ __device__ __forceinline__ void sphere_def(int i, int* pj, int* cj, float* t) {
     *pj = b + 1; *cj = c_child[b]; *t = c_fing_t[k];
 }
 
+// get_sphere_radius (mano_layer.py:271-317), one warp: 16 joint radii from the joints Jr and the
+// mesh, 66 sphere centres from the joints Jc (calculate_coll passes the same joints for both,
+// seg_pcl two different sets, :407-408).  All pointers are per-warp shared-memory scratch.
+__device__ __forceinline__ float build_sphere_set(const float* Jc, const float* Jr, const float* __restrict__ Mg,
+                                                  const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
+                                                  const float* __restrict__ jr_w, int lane, float* s_dist,
+                                                  float* s_jr, float* s_rg, float* s_c, float* s_r, bool* pp_live) {
+    // joint radii: mean of the 10 smallest distances over the regressor support (:275-280)
+    for (int j = 0; j < NJ; ++j) {
+        const float jx = Jr[3 * j], jy = Jr[3 * j + 1], jz = Jr[3 * j + 2];
+        const int e0 = jr_ptr[j], e1 = jr_ptr[j + 1];
+        for (int e = e0 + lane; e < e1; e += 32) {
+            float d = INFINITY;
+            if (jr_w[e] > 0.f) {
+                const int v = jr_idx[e];
+                const float dx = jx - Mg[3 * v], dy = jy - Mg[3 * v + 1], dz = jz - Mg[3 * v + 2];
+                d = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
+            }
+            s_dist[e - e0] = d;
+        }
+        __syncwarp();
+        float sum = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+        for (int pick = 0; pick < 10; ++pick) {
+            float best = INFINITY;
+            int bi = -1;
+            for (int e = lane; e < e1 - e0; e += 32) {
+                const float d = s_dist[e];
+                if (d < best) { best = d; bi = e; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob < best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+            }
+            if (bi < 0) {
+                sum += 100.f;            // sentinel of mano_layer.py:279 (non-support vertices)
+            } else {
+                sum += best;
+                const int v = jr_idx[e0 + bi];
+                gx += (jx - Mg[3 * v]) / best;
+                gy += (jy - Mg[3 * v + 1]) / best;
+                gz += (jz - Mg[3 * v + 2]) / best;
+                __syncwarp();
+                if (lane == 0) s_dist[bi] = INFINITY;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            s_jr[j] = sum * 0.1f;
+            s_rg[3 * j] = gx * 0.1f; s_rg[3 * j + 1] = gy * 0.1f; s_rg[3 * j + 2] = gz * 0.1f;
+        }
+        __syncwarp();
+    }
+    if (lane < 5) s_jr[NJ + lane] = s_jr[3 * lane + 3] / 1.5f;         // fingertips (:281)
+    __syncwarp();
+    const float jr0 = s_jr[0] - 0.05f;
+    const float pp = fminf(fmaxf(jr0, 0.01f), 0.4f);                          // palm root radius (:285)
+    *pp_live = jr0 >= 0.01f && jr0 <= 0.4f;
+
+    // 66 spheres
+    for (int i = lane; i < NS; i += 32) {
+        int pj, cj; float t;
+        sphere_def(i, &pj, &cj, &t);
+        const float rp = (pj == 0) ? pp : s_jr[pj];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float a = Jc[3 * pj + c], b = Jc[3 * cj + c];
+            s_c[3 * i + c] = (i == 0) ? a : (b - a) * t + a;
+        }
+        s_r[i] = (i == 0) ? pp : (s_jr[cj] - rp) * t + rp;
+    }
+    __syncwarp();
+
+    return pp;
+}
+
 __global__ void __launch_bounds__(COLL_WARPS * 32)
 coll_kernel(int B, const float* __restrict__ joints, const float* __restrict__ mesh,
             const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx, const float* __restrict__ jr_w,
@@ -86,72 +163,10 @@ coll_kernel(int B, const float* __restrict__ joints, const float* __restrict__ m
     if (lane < NJOUT) s_gjr[w][lane] = 0.f;
     __syncwarp();
 
-    // joint radii: mean of the 10 smallest distances over the regressor support (:275-280)
-    for (int j = 0; j < NJ; ++j) {
-        const float jx = s_J[w][3 * j], jy = s_J[w][3 * j + 1], jz = s_J[w][3 * j + 2];
-        const int e0 = jr_ptr[j], e1 = jr_ptr[j + 1];
-        for (int e = e0 + lane; e < e1; e += 32) {
-            float d = INFINITY;
-            if (jr_w[e] > 0.f) {
-                const int v = jr_idx[e];
-                const float dx = jx - Mg[3 * v], dy = jy - Mg[3 * v + 1], dz = jz - Mg[3 * v + 2];
-                d = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
-            }
-            s_dist[w][e - e0] = d;
-        }
-        __syncwarp();
-        float sum = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-        for (int pick = 0; pick < 10; ++pick) {
-            float best = INFINITY;
-            int bi = -1;
-            for (int e = lane; e < e1 - e0; e += 32) {
-                const float d = s_dist[w][e];
-                if (d < best) { best = d; bi = e; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob < best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
-            }
-            if (bi < 0) {
-                sum += 100.f;            // sentinel of mano_layer.py:279 (non-support vertices)
-            } else {
-                sum += best;
-                const int v = jr_idx[e0 + bi];
-                gx += (jx - Mg[3 * v]) / best;
-                gy += (jy - Mg[3 * v + 1]) / best;
-                gz += (jz - Mg[3 * v + 2]) / best;
-                __syncwarp();
-                if (lane == 0) s_dist[w][bi] = INFINITY;
-                __syncwarp();
-            }
-        }
-        if (lane == 0) {
-            s_jr[w][j] = sum * 0.1f;
-            s_rg[w][3 * j] = gx * 0.1f; s_rg[w][3 * j + 1] = gy * 0.1f; s_rg[w][3 * j + 2] = gz * 0.1f;
-        }
-        __syncwarp();
-    }
-    if (lane < 5) s_jr[w][NJ + lane] = s_jr[w][3 * lane + 3] / 1.5f;         // fingertips (:281)
-    __syncwarp();
-    const float jr0 = s_jr[w][0] - 0.05f;
-    const float pp = fminf(fmaxf(jr0, 0.01f), 0.4f);                          // palm root radius (:285)
-    const bool pp_live = jr0 >= 0.01f && jr0 <= 0.4f;
-
-    // 66 spheres
-    for (int i = lane; i < NS; i += 32) {
-        int pj, cj; float t;
-        sphere_def(i, &pj, &cj, &t);
-        const float rp = (pj == 0) ? pp : s_jr[w][pj];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = s_J[w][3 * pj + c], b = s_J[w][3 * cj + c];
-            s_c[w][3 * i + c] = (i == 0) ? a : (b - a) * t + a;
-        }
-        s_r[w][i] = (i == 0) ? pp : (s_jr[w][cj] - rp) * t + rp;
-    }
-    __syncwarp();
+    bool pp_live;
+    const float pp = build_sphere_set(s_J[w], s_J[w], Mg, jr_ptr, jr_idx, jr_w, lane, s_dist[w], s_jr[w], s_rg[w],
+                                      s_c[w], s_r[w], &pp_live);
+    (void)pp;
 
     // pass 1: row sums and the per-row gate (:378-384)
     float tot_raw = 0.f, tot_gated = 0.f;
@@ -257,4 +272,45 @@ extern "C" int dsf_coll_forward_backward(const DsfMano* h, int batch, const floa
     DSF_REQUIRE(h && joints && mesh && out_loss && per_hand, "null argument");
     DSF_REQUIRE(batch > 0, "batch must be positive");
     return dsf_coll_impl(h, batch, joints, mesh, out_loss, per_hand, g_joints, (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// sphere set as a stand-alone product (for seg_pcl, "next" row f2): centres (B,66,3), radii (B,66)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(COLL_WARPS * 32)
+sphere_set_kernel(int B, const float* __restrict__ joints_c, const float* __restrict__ joints_r,
+                  const float* __restrict__ mesh, const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
+                  const float* __restrict__ jr_w, float* __restrict__ out_c, float* __restrict__ out_r) {
+    __shared__ float s_dist[COLL_WARPS][NV];
+    __shared__ float s_Jc[COLL_WARPS][NJOUT * 3];
+    __shared__ float s_Jr[COLL_WARPS][NJOUT * 3];
+    __shared__ float s_jr[COLL_WARPS][NJOUT];
+    __shared__ float s_rg[COLL_WARPS][NJ * 3];
+    __shared__ float s_c[COLL_WARPS][NS * 3];
+    __shared__ float s_r[COLL_WARPS][NS];
+    const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int hand = blockIdx.x * COLL_WARPS + w;
+    if (hand >= B) return;
+    for (int i = lane; i < NJOUT * 3; i += 32) {
+        s_Jc[w][i] = joints_c[(size_t)hand * NJOUT * 3 + i];
+        s_Jr[w][i] = joints_r[(size_t)hand * NJOUT * 3 + i];
+    }
+    __syncwarp();
+    bool pp_live;
+    (void)build_sphere_set(s_Jc[w], s_Jr[w], mesh + (size_t)hand * NVW * 3, jr_ptr, jr_idx, jr_w, lane, s_dist[w],
+                           s_jr[w], s_rg[w], s_c[w], s_r[w], &pp_live);
+    for (int i = lane; i < NS * 3; i += 32) out_c[(size_t)hand * NS * 3 + i] = s_c[w][i];
+    for (int i = lane; i < NS; i += 32) out_r[(size_t)hand * NS + i] = s_r[w][i];
+}
+
+extern "C" int dsf_sphere_set(const DsfMano* h, int batch, const float* joints_centres, const float* joints_radii,
+                              const float* mesh, float* centres, float* radii, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && joints_centres && joints_radii && mesh && centres && radii, "null argument");
+    DSF_REQUIRE(batch > 0, "batch must be positive");
+    sphere_set_kernel<<<(batch + COLL_WARPS - 1) / COLL_WARPS, COLL_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        batch, joints_centres, joints_radii, mesh, h->jr_ptr, h->jr_idx, h->jr_w, centres, radii);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
 }

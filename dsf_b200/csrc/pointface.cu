@@ -170,12 +170,13 @@ __global__ void __launch_bounds__(PF_THREADS)
 point_face_bwd_kernel(int P, int V, const float* __restrict__ points, const float* __restrict__ verts,
                       const int* __restrict__ faces, const int* __restrict__ idxs,
                       const float* __restrict__ g_dists, float* __restrict__ g_points,
-                      float* __restrict__ g_verts) {
+                      float* __restrict__ g_verts, const int* __restrict__ seg, const int* __restrict__ sub_ptr) {
     const int b = blockIdx.y;
     const int pi = blockIdx.x * PF_THREADS + threadIdx.x;
     if (pi >= P) return;
     const size_t o = (size_t)b * P + pi;
-    const int f = idxs[o];
+    int f = idxs[o];
+    if (seg && f >= 0) f += sub_ptr[seg[o] - 1];          // index local to the point's own face subset
     const float g = g_dists[o];
     V3 z = v3(0.f, 0.f, 0.f), gp = z, g0 = z, g1 = z, g2 = z;
     if (f >= 0 && g != 0.f) {
@@ -241,7 +242,159 @@ extern "C" int dsf_point_face_backward(int batch, int P, int V, int F, const flo
     DSF_CHECK_CUDA(cudaMemsetAsync(g_verts, 0, (size_t)batch * V * 3 * sizeof(float), (cudaStream_t)stream));
     dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
     point_face_bwd_kernel<<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, points, verts, faces, idxs, g_dists,
-                                                                       g_points, g_verts);
+                                                                       g_points, g_verts, nullptr, nullptr);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+
+// ================================================================================================
+// "next" row f2: seg_pcl (render_model/mano_layer.py:404-426) and JointICPLoss / FingerICPLoss
+// (metric/meshLoss.py:356-394) without replicating the mesh 15 times.
+// ================================================================================================
+#define SEG_THREADS 256
+#define NSPH DSF_NSPHERE
+
+// every point -> 0 (palm) or the finger bone 1..15 whose sphere surface is nearest
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_pcl_kernel(int P, const float* __restrict__ points, const float* __restrict__ centres,
+               const float* __restrict__ radii, int* __restrict__ seg) {
+    __shared__ float s_c[NSPH * 3], s_r[NSPH];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < NSPH * 3; i += SEG_THREADS) s_c[i] = centres[(size_t)b * NSPH * 3 + i];
+    for (int i = threadIdx.x; i < NSPH; i += SEG_THREADS) s_r[i] = radii[(size_t)b * NSPH + i];
+    __syncthreads();
+    const int pi = blockIdx.x * SEG_THREADS + threadIdx.x;
+    if (pi >= P) return;
+    const float* pp = points + ((size_t)b * P + pi) * 3;
+    const float x = pp[0], y = pp[1], z = pp[2];
+    float best_palm = INFINITY, best_fing = INFINITY;
+    int id = 0;
+    for (int i = 0; i < NSPH; ++i) {
+        const float dx = x - s_c[3 * i], dy = y - s_c[3 * i + 1], dz = z - s_c[3 * i + 2];
+        const float d = fabsf(sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f) - s_r[i]);
+        if (i < 21) {
+            best_palm = fminf(best_palm, d);
+        } else if (d < best_fing) {            // first minimum, like torch.min
+            best_fing = d;
+            id = i - 21;
+        }
+    }
+    seg[(size_t)b * P + pi] = best_palm < best_fing ? 0 : id / 3 + 1;
+}
+
+extern "C" int dsf_seg_pcl(int batch, int P, const float* points, const float* centres, const float* radii,
+                           int* seg, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && points && centres && radii && seg, "null / empty argument");
+    dim3 grid((P + SEG_THREADS - 1) / SEG_THREADS, batch);
+    seg_pcl_kernel<<<grid, SEG_THREADS, 0, (cudaStream_t)stream>>>(P, points, centres, radii, seg);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// grid (subset k, hand): the points labelled k+1 are compacted into shared memory and scanned
+// against subset k's triangles only; every other point keeps distance 0 / index -1.
+#define JI_THREADS 256
+#define JI_LIST 4096
+
+__global__ void __launch_bounds__(JI_THREADS)
+joint_icp_fwd_kernel(int P, int V, const float* __restrict__ points, const float* __restrict__ verts,
+                     const int* __restrict__ seg, const int* __restrict__ sub_ptr, const int* __restrict__ sub_faces,
+                     float* __restrict__ dists, int* __restrict__ idxs) {
+    __shared__ __align__(16) float s_rec[256 * PF_REC];
+    __shared__ unsigned short s_list[JI_LIST];
+    __shared__ int s_n;
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int f_lo = sub_ptr[k], f_hi = sub_ptr[k + 1];
+    const int* faces = sub_faces + 3 * (size_t)f_lo;
+    const int F = f_hi - f_lo;
+    const float* vb = verts + (size_t)b * V * 3;
+    const int* sg = seg + (size_t)b * P;
+    for (int p0 = 0; p0 < P; p0 += JI_LIST) {
+        const int np = min(JI_LIST, P - p0);
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int q0 = tid & ~31; q0 < np; q0 += JI_THREADS) {          // warp-aggregated compaction
+            const int q = q0 + lane;
+            const bool hit = q < np && sg[p0 + q] == k + 1;
+            const unsigned int m = __ballot_sync(0xffffffffu, hit);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)q;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int e0 = 0; e0 < n; e0 += JI_THREADS) {
+            const int e = e0 + tid;
+            const int pi = e < n ? p0 + (int)s_list[e] : -1;
+            V3 p = v3(0.f, 0.f, 0.f);
+            if (pi >= 0) p = v3(points[((size_t)b * P + pi) * 3], points[((size_t)b * P + pi) * 3 + 1],
+                                points[((size_t)b * P + pi) * 3 + 2]);
+            float best = INFINITY;
+            int bi = -1;
+            for (int f0 = 0; f0 < F; f0 += 256) {
+                const int nf = min(256, F - f0);
+                __syncthreads();
+                if (tid < nf) build_face_record(vb, faces, f0 + tid, s_rec + tid * PF_REC);
+                __syncthreads();
+                for (int f = 0; f < nf; ++f) {
+                    const float4* r4 = reinterpret_cast<const float4*>(s_rec + f * PF_REC);
+                    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+                    const V3 v0 = v3(q0.x, q0.y, q0.z), e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
+                    const V3 nh = v3(q2.y, q2.z, q2.w);
+                    const V3 a = p - v0;
+                    const float t = -dot(a, nh);
+                    const V3 c = a + nh * t;
+                    const float d20 = dot(c, e1), d21 = dot(c, e2);
+                    const float w1 = (q3.z * d20 - q3.y * d21) * q3.w;
+                    const float w2 = (q3.x * d21 - q3.y * d20) * q3.w;
+                    const float w0 = 1.f - w1 - w2;
+                    float d;
+                    if (q4.w != 0.f && w0 >= 0.f && w0 <= 1.f && w1 >= 0.f && w1 <= 1.f && w2 >= 0.f && w2 <= 1.f) {
+                        d = t * t;
+                    } else {
+                        d = fminf(fminf(seg_d2(a, e1, q4.x), seg_d2(a, e2, q4.y)), seg_d2(a - e1, e2 - e1, q4.z));
+                    }
+                    if (d < best) { best = d; bi = f0 + f; }
+                }
+            }
+            if (pi >= 0) {
+                dists[(size_t)b * P + pi] = best;
+                idxs[(size_t)b * P + pi] = bi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int dsf_joint_icp_forward(int batch, int P, int V, int n_subsets, const float* points, const float* verts,
+                                     const int* seg, const int* subset_ptr, const int* subset_faces, float* dists,
+                                     int* idxs, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(points && verts && seg && subset_ptr && subset_faces && dists && idxs, "null argument");
+    DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0 && n_subsets > 0, "sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSF_CHECK_CUDA(cudaMemsetAsync(dists, 0, (size_t)batch * P * sizeof(float), st));
+    DSF_CHECK_CUDA(cudaMemsetAsync(idxs, 0xFF, (size_t)batch * P * sizeof(int), st));
+    dim3 grid(n_subsets, batch);
+    joint_icp_fwd_kernel<<<grid, JI_THREADS, 0, st>>>(P, V, points, verts, seg, subset_ptr, subset_faces, dists, idxs);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+extern "C" int dsf_joint_icp_backward(int batch, int P, int V, const float* points, const float* verts,
+                                      const int* seg, const int* subset_ptr, const int* subset_faces,
+                                      const int* idxs, const float* g_dists, float* g_points, float* g_verts,
+                                      dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(points && verts && seg && subset_ptr && subset_faces && idxs && g_dists && g_verts, "null argument");
+    DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0, "sizes");
+    DSF_CHECK_CUDA(cudaMemsetAsync(g_verts, 0, (size_t)batch * V * 3 * sizeof(float), (cudaStream_t)stream));
+    dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
+    point_face_bwd_kernel<<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, points, verts, subset_faces, idxs,
+                                                                       g_dists, g_points, g_verts, seg, subset_ptr);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

@@ -320,6 +320,33 @@ class MANO_SMPL(nn.Module):
     def calculate_coll(self, joints, meshs):
         return _CollFunction.apply(self, joints, meshs.detach())
 
+    # -- "next" row f2: sphere set and point-cloud segmentation (no gradient, as used by the trainer) --
+    def _sphere_set(self, joints_c, joints_r, mesh):
+        lib = L.lib()
+        joints_c, joints_r, mesh = L.f32c(joints_c.detach()), L.f32c(joints_r.detach()), L.f32c(mesh.detach())
+        B = joints_c.shape[0]
+        c = torch.empty(B, L.NSPHERE, 3, device=joints_c.device)
+        r = torch.empty(B, L.NSPHERE, device=joints_c.device)
+        L.check(lib.dsf_sphere_set(self._handle, B, joints_c.data_ptr(), joints_r.data_ptr(), mesh.data_ptr(),
+                                   c.data_ptr(), r.data_ptr(), L.stream_ptr()))
+        return c, r
+
+    def get_sphere_radius(self, joints, mesh):
+        """(B,21,3), (B,779,3) -> 66 sphere centres (B,66,3) and radii (B,66) (mano_layer.py:271-317).
+        Forward only; the differentiable use of the spheres is calculate_coll."""
+        return self._sphere_set(joints, joints, mesh)
+
+    def seg_pcl(self, joints, joints_mano, mesh, pcl):
+        """mano_layer.py:404-426: label every point 0 (palm) or 1..15 (finger bone) by the nearest
+        sphere surface; centres from ``joints``, radii from ``joints_mano`` and ``mesh``."""
+        lib = L.lib()
+        c, r = self._sphere_set(joints, joints_mano, mesh)
+        pcl = L.f32c(pcl.detach())
+        B, P, _ = pcl.shape
+        seg = torch.empty(B, P, dtype=torch.int32, device=pcl.device)
+        L.check(lib.dsf_seg_pcl(B, P, pcl.data_ptr(), c.data_ptr(), r.data_ptr(), seg.data_ptr(), L.stream_ptr()))
+        return seg.long()
+
 
 ManoLayer = MANO_SMPL
 

@@ -63,15 +63,67 @@ def ICPLoss(mesh, pcl, faces):
     return point_face_distance(pcl, mesh, faces).mean(-1)
 
 
+class _SubsetPointFaceDistance(torch.autograd.Function):
+    """Every point against the face subset of its own label only (dsf_joint_icp_forward/backward)."""
+
+    @staticmethod
+    def forward(ctx, points, verts, seg_i32, sub_ptr, sub_faces):
+        lib = L.lib()
+        points = L.f32c(points)
+        verts = L.f32c(verts)
+        B, P, _ = points.shape
+        dev = points.device
+        dists = torch.empty(B, P, device=dev)
+        idxs = torch.empty(B, P, dtype=torch.int32, device=dev)
+        L.check(lib.dsf_joint_icp_forward(B, P, verts.shape[1], sub_ptr.numel() - 1, points.data_ptr(),
+                                          verts.data_ptr(), seg_i32.data_ptr(), sub_ptr.data_ptr(),
+                                          sub_faces.data_ptr(), dists.data_ptr(), idxs.data_ptr(), L.stream_ptr()))
+        ctx.save_for_backward(points, verts, seg_i32, sub_ptr, sub_faces, idxs)
+        return dists
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        points, verts, seg_i32, sub_ptr, sub_faces, idxs = ctx.saved_tensors
+        B, P, _ = points.shape
+        gp = torch.empty_like(points)
+        gv = torch.empty_like(verts)
+        g = L.f32c(g)
+        L.check(lib.dsf_joint_icp_backward(B, P, verts.shape[1], points.data_ptr(), verts.data_ptr(),
+                                           seg_i32.data_ptr(), sub_ptr.data_ptr(), sub_faces.data_ptr(),
+                                           idxs.data_ptr(), g.data_ptr(), gp.data_ptr(), gv.data_ptr(),
+                                           L.stream_ptr()))
+        return gp, gv, None, None, None
+
+
+_SUBSET_CACHE = {}
+
+
+def _subset_csr(faces_list, device):
+    key = (tuple(int(f.data_ptr()) for f in faces_list), tuple(int(f.shape[0]) for f in faces_list), str(device))
+    hit = _SUBSET_CACHE.get(key)
+    if hit is None:
+        sizes = [int(f.shape[0]) for f in faces_list]
+        ptr = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32, device=device)
+        faces = torch.cat([_faces_i32(f, device) for f in faces_list], 0).contiguous()
+        hit = (ptr, faces)
+        _SUBSET_CACHE[key] = hit
+    return hit
+
+
 def _part_loss(mesh, pcl, faces_list, pcl_seg):
-    out = []
-    for k, faces in enumerate(faces_list):
-        d = point_face_distance(pcl, mesh, faces)
-        d = torch.where(pcl_seg.eq(k + 1), d, torch.zeros_like(d))
-        valid = d.gt(0).sum(-1)
-        loss = d.sum(-1) / (valid + 1e-8)
-        out.append(torch.where(valid.eq(0), torch.zeros_like(loss), loss))
-    return torch.stack(out, dim=-1)
+    """meshLoss.py:387-394 for all parts at once: the reference replicates mesh and cloud once per
+    part and masks afterwards; here each point only ever meets the faces of its own part."""
+    n = len(faces_list)
+    ptr, faces = _subset_csr(faces_list, pcl.device)
+    seg = pcl_seg.to(torch.int32)
+    seg = torch.where((seg >= 1) & (seg <= n), seg, torch.zeros_like(seg)).contiguous()
+    d = _SubsetPointFaceDistance.apply(pcl, mesh, seg, ptr, faces)                     # (B,P)
+    onehot = torch.nn.functional.one_hot(seg.long(), n + 1)[..., 1:].to(d.dtype)        # (B,P,n)
+    total = torch.einsum("bp,bpk->bk", d, onehot)
+    valid = torch.einsum("bp,bpk->bk", d.gt(0).to(d.dtype), onehot)
+    loss = total / (valid + 1e-8)
+    return torch.where(valid.eq(0), torch.zeros_like(loss), loss)
 
 
 def JointICPLoss(mesh, pcl, faces, pcl_seg):

@@ -157,6 +157,28 @@ int dsf_point_face_backward(int batch, int P, int V, int F, const float* points,
                             const int* faces, const int* idxs, const float* g_dists,
                             float* g_points, float* g_verts, dsfStream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * "next" row f2 - seg_pcl + JointICPLoss.
+ * dsf_sphere_set replaces MANO_SMPL.get_sphere_radius (mano_layer.py:271-317): 66 sphere centres
+ * (B,66,3) from joints_centres and radii (B,66) from joints_radii + mesh (seg_pcl passes two
+ * different joint sets, :407-408).
+ * dsf_seg_pcl replaces MANO_SMPL.seg_pcl (:404-426): points (B,P,3) -> label 0 (palm) or the
+ * finger bone 1..15 whose sphere surface is nearest, seg (B,P) int32.
+ * dsf_joint_icp_forward/backward replace JointICPLoss / FingerICPLoss' distance stage
+ * (metric/meshLoss.py:356-394): each point is tested only against the face subset of its own
+ * label (subset k = label k+1; CSR subset_ptr (n+1), subset_faces (sum,3) device pointers);
+ * other points get distance 0 / index -1, which is what the reference's where() leaves of them. */
+int dsf_sphere_set(const DsfMano* h, int batch, const float* joints_centres, const float* joints_radii,
+                   const float* mesh, float* centres, float* radii, dsfStream_t stream);
+int dsf_seg_pcl(int batch, int P, const float* points, const float* centres, const float* radii, int* seg,
+                dsfStream_t stream);
+int dsf_joint_icp_forward(int batch, int P, int V, int n_subsets, const float* points, const float* verts,
+                          const int* seg, const int* subset_ptr, const int* subset_faces, float* dists,
+                          int* idxs, dsfStream_t stream);
+int dsf_joint_icp_backward(int batch, int P, int V, const float* points, const float* verts, const int* seg,
+                           const int* subset_ptr, const int* subset_faces, const int* idxs,
+                           const float* g_dists, float* g_points, float* g_verts, dsfStream_t stream);
+
 /* device pointer to the handle's face list (n_faces,3) int32, for dsf_point_face_* */
 const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces);
 

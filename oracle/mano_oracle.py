@@ -306,3 +306,15 @@ def crop_hand(img, joint, center, M, cube, intr, offsetxy=25.0, offsetz=20.0, ha
     b = box.view(B, 6, 1, 1)
     mask = (x > b[:, 0]) & (x < b[:, 1]) & (y > b[:, 2]) & (y < b[:, 3]) & (d > b[:, 4]) & (d < b[:, 5])
     return torch.where(mask[:, None], img, torch.ones_like(img)), mask
+
+
+def seg_pcl(c: ManoConstants, joints, joints_mano, mesh, pcl):
+    """mano_layer.py:404-426: 0 = palm, 1..15 = finger bone with the nearest sphere surface."""
+    cen, _ = sphere_set(c, joints, mesh)
+    _, rad = sphere_set(c, joints_mano, mesh)
+    fd = (torch.sqrt(((pcl[:, :, None] - cen[:, None, 21:]) ** 2).sum(-1) + 1e-8) - rad[:, None, 21:]).abs()
+    fmin, fid = fd.min(-1)
+    pd = (torch.sqrt(((pcl[:, :, None] - cen[:, None, :21]) ** 2).sum(-1) + 1e-8) - rad[:, None, :21]).abs()
+    pmin = pd.min(-1)[0]
+    bone = (fid.float() / 3).long() + 1
+    return torch.where(pmin < fmin, torch.zeros_like(bone), bone)

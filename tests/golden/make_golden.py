@@ -98,6 +98,12 @@ def main():
     teacher[:, :, 2] *= 0.6                                  # a tighter z box so the crop actually bites
     crop_out = ld.crop_hand(crop_in.clone(), teacher, center3d, M_d, cube)
 
+    # seg_pcl (mano_layer.py:404-426) on the reference class
+    seg_pts = verts.detach()[:, torch.randint(0, 778, (300,), generator=torch.Generator().manual_seed(11))] \
+        + 0.08 * torch.randn(B, 300, 3, generator=torch.Generator().manual_seed(12))
+    seg_joints = joints.detach() + 0.02 * torch.randn(joints.shape, generator=torch.Generator().manual_seed(13))
+    seg_ref = ref.seg_pcl(seg_joints, joints.detach(), verts.detach(), seg_pts)
+
     out = os.path.join(ROOT, "tests", "golden", "mano_golden.npz")
     np.savez_compressed(
         out,
@@ -113,6 +119,7 @@ def main():
         bounds=torch.stack([xs, xe, ys, ye], 1).numpy(), M=M.numpy(), joint_uvd=joint_uvd.detach().numpy(),
         literal_src=src.numpy().astype(np.int32), zimg=zimg.numpy(), znorm=znorm.numpy(),
         crop_in=crop_in.numpy(), crop_teacher=teacher.numpy(), crop_M=M_d.numpy(), crop_out=crop_out.numpy(),
+        seg_pts=seg_pts.numpy(), seg_joints=seg_joints.numpy(), seg_ref=seg_ref.numpy().astype(np.int32),
     )
     print("crop_hand removed px:", int(((crop_in < 0.99) & (crop_out >= 0.99)).sum()), "of", int((crop_in < 0.99).sum()))
     print("wrote", out, os.path.getsize(out), "bytes")

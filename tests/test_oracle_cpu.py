@@ -128,3 +128,12 @@ def test_crop_hand_matches_reference_loader(golden):
     # of a box face may flip; everything else is identical
     diff = (out != ref)
     assert diff.sum().item() <= 3, diff.sum().item()
+
+
+def test_seg_pcl_matches_reference(golden, mano_model):
+    c = _consts(mano_model)
+    seg = mo.seg_pcl(c, torch.tensor(golden["seg_joints"]), torch.tensor(golden["joints"]),
+                     torch.tensor(golden["verts"]), torch.tensor(golden["seg_pts"]))
+    ref = torch.tensor(golden["seg_ref"]).long()
+    assert len(ref.unique()) > 8, "golden case must hit many parts"
+    assert (seg != ref).sum().item() == 0
