@@ -223,16 +223,12 @@ def run_ours(args):
     step.render_target(host["params_target"].to(dev))
     torch.cuda.synchronize()
     host_target = step.target.cpu().pin_memory()
-    packed = torch.zeros(D.PACK, device=dev)
+    reducer = D.TotalsReducer(dev, B * world)
 
     def one_step():
         step.step()
         if world > 1:
-            # packed loss record: [sum_b per-hand loss * weight, sum |d|, mask count, n_hands]
-            packed[0] = step.totals[0] * B
-            packed[1:3] = step.totals[1:3]
-            packed[3] = float(B)
-            D.allreduce_totals(packed)
+            reducer.submit(step.totals)        # one 16-byte all-reduce per step, overlapped with step i+1
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -240,7 +236,16 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
     with ClockSampler(local) as clk:
-        ms = time_region(one_step, args.steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        if world > 1:
+            reducer.finish()                       # the last collective is inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
         if args.steps * ms < 1500:      # keep the sampler alive long enough to see clocks under load
             time_region(step.step, int(1500 / max(ms, 1e-3)) + 1)    # local work only: no collective
     if world > 1:

@@ -1046,7 +1046,8 @@ depth_loss_totals_kernel(int mode, int B, float weight, const float* __restrict_
         totals[0] = mode == 0 ? weight * u.x / (float)B : t.x / t.y;
         totals[1] = t.x;
         totals[2] = t.y;
-        totals[3] = 0.f;
+        // un-normalised form for cross-rank reduction: global m2d loss = sum_r totals[3] / sum_r B_r
+        totals[3] = mode == 0 ? weight * u.x : t.x;
     }
 }
 

@@ -64,6 +64,35 @@ def global_loss(packed: torch.Tensor) -> torch.Tensor:
     return packed[0] / packed[3]
 
 
+class TotalsReducer:
+    """Per-step all-reduce of a FitStep's ``totals`` record that never stalls the compute stream:
+    the record is copied into one of two rotating buffers and reduced with ``async_op=True`` (NCCL's
+    own stream), so the collective of step i overlaps the kernels of step i+1.  ``totals[3]`` is the
+    un-normalised loss (loss * B_local), hence global loss = reduced[3] / total_hands."""
+
+    def __init__(self, device, total_hands: int):
+        self.bufs = [torch.zeros(PACK, dtype=torch.float32, device=device) for _ in range(2)]
+        self.handles = [None, None]
+        self.total_hands = total_hands
+        self.i = 0
+
+    def submit(self, totals: torch.Tensor):
+        k = self.i & 1
+        if self.handles[k] is not None:
+            self.handles[k].wait()                 # buffer k was last used two steps ago
+        self.bufs[k].copy_(totals, non_blocking=True)
+        self.handles[k] = allreduce_totals(self.bufs[k], async_op=True)
+        self.i += 1
+
+    def finish(self) -> float:
+        """Wait for everything in flight; returns the global loss of the last submitted step."""
+        for h in self.handles:
+            if h is not None:
+                h.wait()
+        last = self.bufs[(self.i - 1) & 1]
+        return float(last[3].item()) / self.total_hands
+
+
 def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -132,7 +132,8 @@ int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* verts_cam, co
  * mode 0: inline m2d loss, train_render.py:728-732  (union mask, per-hand normalised, x weight/B)
  * mode 1: depth_loss.forward, render_model/render_loss.py:15-21 (both < thr, global mean)
  * real/synth (B,R,R).  parts (B,2) = per-hand [sum |d|*mask, count]; totals (4) =
- * [loss, sum, count, 0]; g_synth (B,R,R) or NULL = d loss / d synth. */
+ * [loss, sum, count, loss * B (un-normalised, for summing over ranks)];
+ * g_synth (B,R,R) or NULL = d loss / d synth. */
 int dsf_depth_loss(int mode, int batch, int R, const float* real, const float* synth, float thr,
                    float weight, float* parts, float* totals, float* g_synth, dsfStream_t stream);
 

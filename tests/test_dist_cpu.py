@@ -38,7 +38,11 @@ def _worker(rank, world, port, total, out):
     packed = D.pack_totals(per_hand.mean() * n, per_hand.sum(), torch.tensor(float(n * 3)), n)
     D.allreduce_totals(packed)
     t = D.max_over_ranks(float(rank + 1), torch.device("cpu"))
-    out[rank] = (packed.tolist(), D.global_loss(packed).item(), t)
+    # the overlapped per-step reducer: totals = [loss, sum, count, loss * n_local]
+    red = D.TotalsReducer(torch.device("cpu"), total)
+    for it in range(3):
+        red.submit(torch.tensor([per_hand.mean(), per_hand.sum(), float(n * 3), per_hand.mean() * n]) * (it + 1))
+    out[rank] = (packed.tolist(), D.global_loss(packed).item(), t, red.finish())
     dist.destroy_process_group()
 
 
@@ -49,7 +53,8 @@ def test_packed_allreduce_world2_gloo():
     mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
     ref = torch.arange(total, dtype=torch.float32) * 0.01
     for r in range(world):
-        packed, loss, t = out[r]
+        packed, loss, t, red_loss = out[r]
+        assert abs(red_loss - 3 * ref.mean().item()) < 1e-5
         assert abs(packed[1] - ref.sum().item()) < 1e-4
         assert packed[2] == total * 3 and packed[3] == total
         assert abs(loss - ref.mean().item()) < 1e-5
