@@ -167,7 +167,7 @@ def stage_times(step, iters=10):
     lib = L.lib()
     B, R, h = step.B, step.R, step.layer._handle
     s = L.stream_ptr()
-    ws = step.ws
+    ws = step.ws[0]
     g_img = torch.zeros(B, R, R, device=step.dev)
     g_verts = torch.zeros(B, 779, 3, device=step.dev)
     vcam = (step.verts * step.cube[:, None] / 2 + step.center3d[:, None]).contiguous()
@@ -218,7 +218,7 @@ def run_ours(args):
     layer = MANO_SMPL(make_synthetic_mano(0), "nyu")
     inp = sample_fit_inputs(B, seed=1000 + rank)
     host = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
-    step = FitStep(layer, B, CROP, use_graph=not args.no_graph)
+    step = FitStep(layer, B, CROP, use_graph=not args.no_graph, chunks=args.chunks)
     step.set_inputs(host["params"].to(dev), host["center3d"].to(dev), host["cube"].to(dev))
     step.render_target(host["params_target"].to(dev))
     torch.cuda.synchronize()
@@ -258,7 +258,7 @@ def run_ours(args):
     # every step: H2D of that step's inputs (params, centre, cube, target depth) from pinned memory,
     # the fused step, D2H of loss + parameter gradients.  Two FitStep instances ping-pong so the copy
     # of step i+1 (copy stream) overlaps the compute of step i; all copies stay inside the timed region.
-    steps2 = [step, FitStep(layer, B, CROP, use_graph=not args.no_graph)]
+    steps2 = [step, FitStep(layer, B, CROP, use_graph=not args.no_graph, chunks=args.chunks)]
     h_g = [torch.empty(B, 62).pin_memory() for _ in range(2)]
     h_tot = [torch.empty(4).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
@@ -393,7 +393,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-        "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph,
+        "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph, "stream_chunks": args.chunks,
         "roofline": roofline, "cpu_baseline": cpu, "loss": float(step.totals[0]), "other_configs": other,
     }
     print(json.dumps(line), flush=True)
@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32, help="hands per CPU reference step (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--chunks", type=int, default=2, help="slices of the batch run on parallel streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()

@@ -72,7 +72,7 @@ SIGNATURES = {
     "dsf_joint_icp_forward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_joint_icp_backward": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_fit_workspace_floats": (_L, [_I, _I]),
-    "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _I, _VP, c_float_p,
+    "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I, _VP, _I, _VP, c_float_p,
                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_crop_hand": (_I, [_I, _I, _VP, _VP, _I, _VP, _VP, _VP, c_float_p, _F, _F, _F, _VP, _VP, _VP]),
 }

@@ -36,7 +36,8 @@ extern "C" long dsf_fit_workspace_floats(int batch, int R) {
 
 extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
                             const float* cube, const float* view, const float* xs, const float* ys,
-                            const float* target, float loss_weight, const float* crop_joints, int n_crop_joints,
+                            const float* target, float loss_weight, int norm_batch, const float* crop_joints,
+                            int n_crop_joints,
                             const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                             float* verts, float* joints, float* g_params, float* parts, float* totals,
                             float* workspace, dsfStream_t stream) {
@@ -80,7 +81,8 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     if (rc) return rc;
     // backward recomputes d loss / d img per pixel from (target, img, N_b): no gradient image in HBM
     rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, nullptr,
-                                  g_verts, target, img, parts, loss_weight / (float)batch, thr, cropp, st);
+                                  g_verts, target, img, parts, loss_weight / (float)(norm_batch > 0 ? norm_batch : batch), thr,
+                                  cropp, st);
     if (rc) return rc;
     rc = dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
     return rc;

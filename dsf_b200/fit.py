@@ -14,7 +14,7 @@ from . import _lib as L
 
 class FitStep:
     def __init__(self, mano_layer, batch, crop=128, cam_para=(588.03, 587.07, 320.0, 240.0),
-                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None):
+                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None, chunks=1):
         self.lib = L.lib()
         self.layer = mano_layer
         self.B, self.R = int(batch), int(crop)
@@ -40,7 +40,18 @@ class FitStep:
         self.g_params = f(B, 62)
         self.parts = f(B, 2)
         self.totals = f(4)
-        self.ws = f(self.lib.dsf_fit_workspace_floats(B, R))
+        # the batch can be cut into `chunks` slices that run the kernel chain on parallel streams
+        # (hands are independent): the tail of one slice's kernels overlaps the next slice's heads
+        self.chunks = max(1, min(int(chunks), B))
+        base, rem = divmod(B, self.chunks)
+        self._bounds, lo = [], 0
+        for c in range(self.chunks):
+            hi = lo + base + (1 if c < rem else 0)
+            self._bounds.append((lo, hi))
+            lo = hi
+        self.ws = [f(self.lib.dsf_fit_workspace_floats(hi - lo, R)) for lo, hi in self._bounds]
+        self.chunk_totals = f(self.chunks, 4)
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.chunks - 1)]
         self.crop_joints = None          # (B,J,3) teacher joints -> crop_hand before the loss
         self.use_graph = use_graph
         self._graph = None
@@ -69,15 +80,36 @@ class FitStep:
                                         self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
                                         self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), s))
         n += self.lib.dsf_last_launch_count()
-        L.check(self.lib.dsf_fit_step(self.layer._handle, self.B, self.R, self.params.data_ptr(),
-                                      self.center3d.data_ptr(), self.cube.data_ptr(), self.view.data_ptr(),
-                                      self.xs.data_ptr(), self.ys.data_ptr(), self.target.data_ptr(),
-                                      self.loss_weight, L.ptr(self.crop_joints),
-                                      0 if self.crop_joints is None else self.crop_joints.shape[1],
-                                      self.M.data_ptr(), self._intr, self.img.data_ptr(), self.p2f.data_ptr(),
-                                      self.verts.data_ptr(), self.joints.data_ptr(), self.g_params.data_ptr(),
-                                      self.parts.data_ptr(), self.totals.data_ptr(), self.ws.data_ptr(), s))
-        n += self.lib.dsf_last_launch_count()
+        nj = 0 if self.crop_joints is None else self.crop_joints.shape[1]
+        R2 = self.R * self.R
+
+        def run_chunk(c):
+            lo, hi = self._bounds[c]
+            off = lambda t, per: t.data_ptr() + lo * per * t.element_size()
+            L.check(self.lib.dsf_fit_step(
+                self.layer._handle, hi - lo, self.R, off(self.params, 62), off(self.center3d, 3),
+                off(self.cube, 3), off(self.view, L.VIEW_STRIDE), off(self.xs, self.R), off(self.ys, self.R),
+                off(self.target, R2), self.loss_weight, self.B,
+                None if self.crop_joints is None else off(self.crop_joints, nj * 3), nj, off(self.M, 9),
+                self._intr, off(self.img, R2), off(self.p2f, R2), off(self.verts, L.NVW * 3),
+                off(self.joints, L.NJOUT * 3), off(self.g_params, 62), off(self.parts, 2),
+                self.chunk_totals[c].data_ptr(), self.ws[c].data_ptr(), L.stream_ptr()))
+            return self.lib.dsf_last_launch_count()
+
+        main = torch.cuda.current_stream()
+        for c, st in enumerate(self._streams, start=1):        # fork
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                n += run_chunk(c)
+        n += run_chunk(0)
+        for st in self._streams:                                # join
+            main.wait_stream(st)
+        # totals of the whole batch from the per-slice records ([3] is the un-normalised loss)
+        if self.chunks == 1:
+            self.totals.copy_(self.chunk_totals[0])
+        else:
+            ssum = self.chunk_totals.sum(0)
+            self.totals.copy_(torch.stack([ssum[3] / self.B, ssum[1], ssum[2], ssum[3]]))
         self.launches_per_step = n
 
     def step(self):

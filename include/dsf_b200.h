@@ -187,14 +187,17 @@ const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces);
  * Fused fitting step: M1+M4 -> R1/R4 -> L2 -> R2 -> MANO backward, one call, fixed launch
  * sequence (graph-capturable).  params (B,62) = [quat3|theta45|beta10|scale|trans3]; target
  * (B,R,R) normalised depth; view/xs/ys from dsf_view_setup; cube (B,3), center3d (B,3).
+ * norm_batch: the number of hands the batch mean of the loss runs over (<= 0: batch); a caller that
+ * splits one batch into several calls (e.g. on parallel streams) passes the full size so the
+ * gradients are scaled alike, and combines totals[3] (un-normalised loss) itself.
  * crop_joints (B,n,3) or NULL: teacher joints for crop_hand of the rendered image before the loss.
  * Outputs: img (B,R,R), pix_to_face (B,R,R), verts (B,779,3), joints (B,21,3) (normalised cube
  * units, global_scale 1/125), g_params (B,62) = d loss/d params, parts (B,2), totals (4). */
 long dsf_fit_workspace_floats(int batch, int R);
 int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
                  const float* cube, const float* view, const float* xs, const float* ys,
-                 const float* target, float loss_weight, const float* crop_joints, int n_crop_joints,
-                 const float* crop_M, const float* intr4, float* img, int* pix_to_face,
+                 const float* target, float loss_weight, int norm_batch, const float* crop_joints,
+                 int n_crop_joints, const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
                  float* workspace, dsfStream_t stream);
 

@@ -17,7 +17,7 @@ step = FitStep(layer, B, R, use_graph=False)
 step.set_inputs(inp["params"].cuda(), inp["center3d"].cuda(), inp["cube"].cuda(), tgt_ref.detach().cuda())
 step.step(); torch.cuda.synchronize()
 PER = 6708
-ws = step.ws[:B * PER].view(B, PER).double().cpu()
+ws = step.ws[0][:B * PER].view(B, PER).double().cpu()
 GVP = ws[:, 2996:2996 + 2336]
 GX = ws[:, 5524:5524 + 8 * 148].view(B, 8, 148).sum(1)
 X = ws[:, 0:148]; VP = ws[:, 148:148 + 2336]
