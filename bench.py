@@ -96,9 +96,13 @@ def cpu_pipeline(batch: int, seed: int = 0):
     torch.set_num_threads(cores)
     consts = mo.ManoConstants(make_synthetic_mano(0))
     inp = {k: torch.from_numpy(v) for k, v in sample_fit_inputs(batch, seed=seed).items()}
+    from dsf_b200.synthetic import quantise_depth_mm
     with torch.no_grad():
         target, *_ = pl.render(consts, inp["params_target"], inp["center3d"], inp["cube"])
-    target = target.detach()
+    # same workload definition as the GPU arm: the target is what a depth sensor delivers (integer mm),
+    # normalised the way the reference's loader does it on the CPU (data/render_loader.py:738-745)
+    mm = quantise_depth_mm(target.detach(), inp["center3d"], inp["cube"])
+    target = mo.target_from_u16(mm.to(torch.int32), inp["center3d"], inp["cube"])
 
     def step():
         return pl.fit_step(consts, inp["params"], inp["center3d"], inp["cube"], target)
@@ -139,6 +143,7 @@ def workload_config(args, world):
                     f"128x128 depth, direct crop raster, NYU intrinsics, synthetic hand-shaped MANO (778v/1554f)",
         "hands_per_gpu": args.batch, "global_batch": args.batch * world, "crop": CROP, "views": 1,
         "parallelism": f"batch-sharded x{world}",
+        "target": "rendering of a perturbed parameter set, quantised to integer millimetres like sensor depth",
         "l2_policy": "inputs larger than L2 (target+rendered images %.0f MB per step vs 126 MB L2)"
                      % (2 * args.batch * CROP * CROP * 4 / 1e6),
     }
@@ -221,8 +226,14 @@ def run_ours(args):
     step = FitStep(layer, B, CROP, use_graph=not args.no_graph, chunks=args.chunks)
     step.set_inputs(host["params"].to(dev), host["center3d"].to(dev), host["cube"].to(dev))
     step.render_target(host["params_target"].to(dev))
+    # the target is what a depth sensor delivers: integer millimetres.  It is resident (normalised fp32) for
+    # `value`; for `e2e` it travels every step either as the sensor's uint16 (normalised on the device,
+    # the default) or as the loader-normalised fp32 image the reference uploads (--target-format f32).
+    from dsf_b200.synthetic import quantise_depth_mm
+    mm = quantise_depth_mm(step.target, step.center3d, step.cube)
+    step.set_inputs(step.params, step.center3d, step.cube, mm)
     torch.cuda.synchronize()
-    host_target = step.target.cpu().pin_memory()
+    host_targets = {"u16": mm.cpu().pin_memory(), "f32": step.target.cpu().pin_memory()}
     reducer = D.TotalsReducer(dev, B * world)
 
     def one_step():
@@ -266,48 +277,58 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
 
-    def upload(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[i])            # buffers of slot i are free again
-            steps2[i].set_inputs(host["params"], host["center3d"], host["cube"], host_target)
-            ready[i].record(copy_stream)
-
-    for st_ in steps2:                                   # warm both graphs
-        st_.set_inputs(host["params"], host["center3d"], host["cube"], host_target)
-        st_.step()
-    torch.cuda.synchronize()
-    for i in range(2):
-        done[i].record(main_stream)
     e2e_iters = max(4, min(args.steps, 20))
-
-    def e2e_run():
-        upload(0)
-        for it in range(e2e_iters):
-            i = it & 1
-            if it + 1 < e2e_iters:
-                upload(1 - i)
-            main_stream.wait_event(ready[i])
-            steps2[i].step()
-            h_g[i].copy_(steps2[i].g_params, non_blocking=True)
-            h_tot[i].copy_(steps2[i].totals, non_blocking=True)
-            done[i].record(main_stream)
-        main_stream.synchronize()
-
-    e2e_run()
-    if world > 1:
-        torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    e2e_run()
-    e1.record()
-    torch.cuda.synchronize()
-    t_e2e = D.max_over_ranks(e0.elapsed_time(e1) / e2e_iters, dev)
-    h2d = B * (62 + 3 + 3 + CROP * CROP) * 4
     d2h = B * 62 * 4 + 16
-    e2e = {"value": B * world / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": d2h * world, "ms_per_step": t_e2e,
-           "note": "double-buffered: H2D of step i+1 overlaps compute of step i; PCIe-bound (%.0f MB in per step)" % (h2d / 1e6)}
+
+    def measure_e2e(fmt):
+        host_target = host_targets[fmt]
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i])            # buffers of slot i are free again
+                steps2[i].set_inputs(host["params"], host["center3d"], host["cube"], host_target)
+                ready[i].record(copy_stream)
+
+        for st_ in steps2:                                   # warm both graphs
+            st_.set_inputs(host["params"], host["center3d"], host["cube"], host_target)
+            st_.step()
+        torch.cuda.synchronize()
+        for i in range(2):
+            done[i].record(main_stream)
+
+        def e2e_run():
+            upload(0)
+            for it in range(e2e_iters):
+                i = it & 1
+                if it + 1 < e2e_iters:
+                    upload(1 - i)
+                main_stream.wait_event(ready[i])
+                steps2[i].step()
+                h_g[i].copy_(steps2[i].g_params, non_blocking=True)
+                h_tot[i].copy_(steps2[i].totals, non_blocking=True)
+                done[i].record(main_stream)
+            main_stream.synchronize()
+
+        e2e_run()
+        if world > 1:
+            torch.distributed.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        e2e_run()
+        e1.record()
+        torch.cuda.synchronize()
+        t = D.max_over_ranks(e0.elapsed_time(e1) / e2e_iters, dev)
+        h2d = B * (62 + 3 + 3) * 4 + B * CROP * CROP * (2 if fmt == "u16" else 4)
+        return {"value": B * world / (t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": t, "target_format": fmt,
+                "note": "double-buffered: H2D of step i+1 overlaps compute of step i; PCIe-bound (%.0f MB in per "
+                        "step); target crop travels as %s" % (h2d / 1e6, "the sensor's uint16 mm, normalised on the "
+                        "device (dsf_target_from_u16)" if fmt == "u16" else "loader-normalised fp32")}
+
+    e2e = measure_e2e(args.target_format)
+    alt_fmt = "f32" if args.target_format == "u16" else "u16"
+    e2e_alt = measure_e2e(alt_fmt)
 
     if rank != 0:
         return
@@ -395,6 +416,7 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
         "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph, "stream_chunks": args.chunks,
         "roofline": roofline, "cpu_baseline": cpu, "loss": float(step.totals[0]), "other_configs": other,
+        "e2e_%s_target" % alt_fmt: e2e_alt,
     }
     print(json.dumps(line), flush=True)
 
@@ -410,6 +432,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--chunks", type=int, default=2, help="slices of the batch run on parallel streams")
+    ap.add_argument("--target-format", choices=["u16", "f32"], default="u16",
+                    help="how the target depth crop travels host->device in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()

@@ -1,0 +1,326 @@
+// dsf_b200 - depth crop -> point cloud for sm_100a ("next" row f1 of SURVEY.md section 8).
+// Replaces loader.Img2pcl (data/render_loader.py:1121-1156: nearest resize, `<= 0.99` foreground
+// mask, a Python loop over the batch with masked_select + multinomial) and loader.uvdImg2xyzImg
+// (:1190-1200) with uvd_nl2xyznl_tensor / uvd_nl2xyz_tensor (:1044-1073), get_trans_points
+// (:1113-1118) and pointsImgTo3D (:336-343).
+//
+// One CTA per hand, no host round trip: count the foreground pixels, choose `sample_num mod n`
+// of them without replacement by taking the smallest counter-based hash keys (3-pass radix select
+// in shared memory), and write [the whole foreground list repeated floor(sample_num / n) times |
+// the chosen ones], both in pixel order, exactly the layout :1141-1153 produces.  The sampled
+// subset is uniform and reproducible from `seed`; it is not torch.multinomial's stream (the
+// consumers - ICP losses and seg_pcl - are permutation invariant).
+#include <math.h>
+
+#include "common.cuh"
+
+#define PCL_THREADS 512
+#define PCL_WARPS (PCL_THREADS / 32)
+#define PCL_BINS 4096
+
+struct PclView {
+    float mi[9];              // inverse of the crop transform M
+    float cx, cy, cz;         // center3d
+    float hx, hy, hz;         // cube / 2
+    float fx, fy, px, py, flip;
+    float half_img;           // loader.img_size / 2
+};
+
+__device__ __forceinline__ void pcl_view_load(PclView* v, int b, const float* center, const float* cube, const float* M,
+                                              const float* intr4, float img_size, float flip) {
+    const float* m = M + 9 * (size_t)b;
+    const float a = m[0], bb = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const float c00 = e * i - f * h, c01 = f * g - d * i, c02 = d * h - e * g;
+    const float det = a * c00 + bb * c01 + c * c02;
+    const float r = 1.f / det;
+    v->mi[0] = c00 * r; v->mi[1] = (c * h - bb * i) * r; v->mi[2] = (bb * f - c * e) * r;
+    v->mi[3] = c01 * r; v->mi[4] = (a * i - c * g) * r;  v->mi[5] = (c * d - a * f) * r;
+    v->mi[6] = c02 * r; v->mi[7] = (bb * g - a * h) * r; v->mi[8] = (a * e - bb * d) * r;
+    v->cx = center[3 * b]; v->cy = center[3 * b + 1]; v->cz = center[3 * b + 2];
+    v->hx = __fdiv_rn(cube[3 * b], 2.f); v->hy = __fdiv_rn(cube[3 * b + 1], 2.f); v->hz = __fdiv_rn(cube[3 * b + 2], 2.f);
+    v->fx = intr4[0]; v->fy = intr4[1]; v->px = intr4[2]; v->py = intr4[3];
+    v->flip = flip;
+    v->half_img = __fdiv_rn(img_size, 2.f);
+}
+
+// normalised (u, v, d) of grid cell (row, col) -> camera-space mm (uvd_nl2xyz_tensor :1044-1057)
+__device__ __forceinline__ void pcl_point(const PclView& v, int row, int col, int fs, float val, float* xyz) {
+    const float fm1 = (float)fs - 1.f;
+    const float gu = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, (float)col), fm1), 1.f);
+    const float gv = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, (float)row), fm1), 1.f);
+    const float uu = __fmul_rn(__fadd_rn(gu, 1.f), v.half_img), vv = __fmul_rn(__fadd_rn(gv, 1.f), v.half_img);
+    const float d = __fadd_rn(__fmul_rn(val, v.hz), v.cz);
+    const float us = __fadd_rn(__fadd_rn(__fmul_rn(v.mi[0], uu), __fmul_rn(v.mi[1], vv)), v.mi[2]);
+    const float vs = __fadd_rn(__fadd_rn(__fmul_rn(v.mi[3], uu), __fmul_rn(v.mi[4], vv)), v.mi[5]);
+    xyz[0] = __fdiv_rn(__fmul_rn(__fsub_rn(us, v.px), d), v.fx);
+    xyz[1] = __fdiv_rn(__fmul_rn(__fmul_rn(v.flip, __fsub_rn(vs, v.py)), d), v.fy);
+    xyz[2] = d;
+}
+
+__device__ __forceinline__ void pcl_normalise(const PclView& v, const float* xyz, float* out) {
+    out[0] = __fdiv_rn(__fsub_rn(xyz[0], v.cx), v.hx);
+    out[1] = __fdiv_rn(__fsub_rn(xyz[1], v.cy), v.hy);
+    out[2] = __fdiv_rn(__fsub_rn(xyz[2], v.cz), v.hz);
+}
+
+// F.interpolate(mode="nearest"): source index = min(floor(dst * in / out), in - 1)
+__device__ __forceinline__ int nearest_src(int dst, int n_in, float scale) {
+    const int s = (int)floorf(__fmul_rn((float)dst, scale));
+    return s < n_in - 1 ? s : n_in - 1;
+}
+
+__device__ __forceinline__ unsigned pcl_key(unsigned long long seed, unsigned hand, unsigned pix) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)hand << 32) | pix);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (unsigned)(z >> 32);
+}
+
+__device__ __forceinline__ int block_sum(int v, int* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int w = 0; w < PCL_WARPS; ++w) t += s_red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(PCL_THREADS)
+img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __restrict__ center,
+               const float* __restrict__ cube, const float* __restrict__ M, float4 intr, float img_size, float flip,
+               int sample_num, unsigned long long seed, int out_rows, float* __restrict__ pcl, int* __restrict__ count) {
+    __shared__ PclView view;
+    __shared__ int s_hist[PCL_BINS];
+    __shared__ int s_red[PCL_WARPS];
+    __shared__ int s_scan[3][PCL_WARPS];
+    __shared__ int s_sel[3];          // chosen bin, items below it, (unused)
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npix = fs * fs;
+    const float* im = img + (size_t)b * R_in * R_in;
+    const float scale = (float)R_in / (float)fs;
+    if (tid == 0) {
+        const float in4[4] = {intr.x, intr.y, intr.z, intr.w};
+        pcl_view_load(&view, b, center, cube, M, in4, img_size, flip);
+    }
+    auto value = [&](int k) -> float {
+        const int row = k / fs, col = k - row * fs;
+        return R_in == fs ? im[k] : im[(size_t)nearest_src(row, R_in, scale) * R_in + nearest_src(col, R_in, scale)];
+    };
+
+    int mine = 0;
+    for (int k = tid; k < npix; k += PCL_THREADS) mine += value(k) <= 0.99f;
+    const int n = block_sum(mine, s_red);          // also publishes `view`
+    if (tid == 0 && count) count[b] = n;
+    float* out = pcl + (size_t)b * out_rows * 3;
+    if (n == 0) {                                  // :1144 - an empty crop gives zeros
+        for (int k = tid; k < out_rows * 3; k += PCL_THREADS) out[k] = 0.f;
+        return;
+    }
+    const int mult = sample_num > 0 ? sample_num / n : 1;
+    const int k_rem = sample_num > 0 ? sample_num - mult * n : 0;
+
+    // k_rem-th smallest key among the foreground pixels: radix select over 12 + 12 + 8 bits
+    unsigned prefix = 0, prefix_mask = 0;
+    int need = k_rem;                              // rank (1-based) still to be located
+    if (k_rem > 0) {
+        const int shifts[3] = {20, 8, 0}, widths[3] = {12, 12, 8};
+        for (int pass = 0; pass < 3; ++pass) {
+            const int nb = 1 << widths[pass];
+            for (int i = tid; i < nb; i += PCL_THREADS) s_hist[i] = 0;
+            __syncthreads();
+            for (int k = tid; k < npix; k += PCL_THREADS) {
+                if (value(k) <= 0.99f) {
+                    const unsigned key = pcl_key(seed, b, k);
+                    if ((key & prefix_mask) == prefix) atomicAdd(&s_hist[(key >> shifts[pass]) & (nb - 1)], 1);
+                }
+            }
+            __syncthreads();
+            // each thread owns nb / 512 consecutive bins (at least one thread-bin for the 256-bin pass)
+            const int per = nb >= PCL_THREADS ? nb / PCL_THREADS : 1;
+            const int b0 = tid * per;
+            int local = 0;
+            if (b0 < nb)
+                for (int i = 0; i < per; ++i) local += s_hist[b0 + i];
+            int incl = local;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_scan[0][warp] = incl;
+            __syncthreads();
+            int before = incl - local;
+            for (int w = 0; w < warp; ++w) before += s_scan[0][w];
+            if (b0 < nb && before < need && need <= before + local) {
+                int cum = before;
+                for (int i = 0; i < per; ++i) {
+                    const int h = s_hist[b0 + i];
+                    if (need <= cum + h) { s_sel[0] = b0 + i; s_sel[1] = cum; break; }
+                    cum += h;
+                }
+            }
+            __syncthreads();
+            prefix |= (unsigned)s_sel[0] << shifts[pass];
+            prefix_mask |= (unsigned)(nb - 1) << shifts[pass];
+            need -= s_sel[1];
+            __syncthreads();
+        }
+    }
+    const unsigned thr = prefix;                   // keys < thr are all taken, `need` of the keys == thr
+
+    // ordered compaction
+    int base_valid = 0, base_less = 0, base_eq = 0;
+    for (int k0 = 0; k0 < npix; k0 += PCL_THREADS) {
+        const int k = k0 + tid;
+        float val = 1.f;
+        bool v = false, less = false, eq = false;
+        if (k < npix) {
+            val = value(k);
+            v = val <= 0.99f;
+            if (v && k_rem > 0) {
+                const unsigned key = pcl_key(seed, b, k);
+                less = key < thr;
+                eq = key == thr;
+            }
+        }
+        const unsigned mv = __ballot_sync(0xffffffffu, v), ml = __ballot_sync(0xffffffffu, less),
+                       me = __ballot_sync(0xffffffffu, eq);
+        const unsigned lower = (1u << lane) - 1u;
+        __syncthreads();
+        if (lane == 0) { s_scan[0][warp] = __popc(mv); s_scan[1][warp] = __popc(ml); s_scan[2][warp] = __popc(me); }
+        __syncthreads();
+        int rv = base_valid + __popc(mv & lower), rl = base_less + __popc(ml & lower), re = base_eq + __popc(me & lower);
+        int tv = 0, tl = 0, te = 0;
+        for (int w = 0; w < PCL_WARPS; ++w) {
+            const int a = s_scan[0][w], c = s_scan[1][w], e = s_scan[2][w];
+            if (w < warp) { rv += a; rl += c; re += e; }
+            tv += a; tl += c; te += e;
+        }
+        if (v) {
+            const int row = k / fs, col = k - row * fs;
+            float xyz[3], q[3];
+            pcl_point(view, row, col, fs, val, xyz);
+            pcl_normalise(view, xyz, q);
+            for (int m = 0; m < mult; ++m) {
+                float* o = out + ((size_t)m * n + rv) * 3;
+                o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+            }
+            // selected rank in pixel order: all `less` so far plus the admitted ties so far
+            const bool take = less || (eq && re < need);
+            if (take) {
+                const int r = rl + (re < need ? re : need);
+                float* o = out + ((size_t)mult * n + r) * 3;
+                o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+            }
+        }
+        base_valid += tv; base_less += tl; base_eq += te;
+    }
+}
+
+extern "C" int dsf_img2pcl(int batch, int R_in, int feature_size, const float* img, const float* center3d,
+                           const float* cube, const float* M, const float* intr4, float img_size, float flip,
+                           int sample_num, unsigned long long seed, float* pcl, int* count, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && img && center3d && cube && M && intr4 && pcl, "null / empty argument");
+    DSF_REQUIRE(R_in >= 2 && feature_size >= 2 && feature_size <= 1024, "feature_size must be in [2,1024]");
+    DSF_REQUIRE(sample_num >= 0, "sample_num must be >= 0");
+    const int out_rows = sample_num > 0 ? sample_num : feature_size * feature_size;
+    img2pcl_kernel<<<batch, PCL_THREADS, 0, (cudaStream_t)stream>>>(
+        R_in, feature_size, img, center3d, cube, M, make_float4(intr4[0], intr4[1], intr4[2], intr4[3]), img_size, flip,
+        sample_num, seed, out_rows, pcl, count);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// uvdImg2xyzImg (:1190-1200): per pixel camera-space xyz (mm) and the cube-normalised copy, both (B,3,R,R)
+__global__ void __launch_bounds__(256)
+uvd_img_to_xyz_kernel(int R, const float* __restrict__ img, const float* __restrict__ center,
+                      const float* __restrict__ cube, const float* __restrict__ M, float4 intr, float img_size, float flip,
+                      float* __restrict__ xyz_img, float* __restrict__ xyz_normal) {
+    __shared__ PclView view;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const float in4[4] = {intr.x, intr.y, intr.z, intr.w};
+        pcl_view_load(&view, b, center, cube, M, in4, img_size, flip);
+    }
+    __syncthreads();
+    const int npix = R * R;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= npix) return;
+    float xyz[3], q[3];
+    pcl_point(view, k / R, k % R, R, img[(size_t)b * npix + k], xyz);
+    pcl_normalise(view, xyz, q);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (xyz_img) xyz_img[((size_t)b * 3 + c) * npix + k] = xyz[c];
+        if (xyz_normal) xyz_normal[((size_t)b * 3 + c) * npix + k] = q[c];
+    }
+}
+
+extern "C" int dsf_uvd_img_to_xyz(int batch, int R, const float* img, const float* center3d, const float* cube,
+                                  const float* M, const float* intr4, float img_size, float flip, float* xyz_img,
+                                  float* xyz_normal, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && R >= 2 && img && center3d && cube && M && intr4 && (xyz_img || xyz_normal),
+                "null / empty argument");
+    dim3 grid((R * R + 255) / 256, batch);
+    uvd_img_to_xyz_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        R, img, center3d, cube, M, make_float4(intr4[0], intr4[1], intr4[2], intr4[3]), img_size, flip, xyz_img,
+        xyz_normal);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sensor depth crop -> normalised target on the device.  The reference's loader crops the uint16
+// millimetre depth map with INTER_NEAREST (data/render_loader.py:406,795), normalises it on the CPU
+// (normalize_img :738-745) and ships 4 bytes per pixel to the GPU; here the crop travels as the
+// sensor's own uint16 (half the PCIe bytes) and :738-745 runs in this kernel, same operation order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float target_norm(unsigned u, unsigned invalid, float cz, float hz, float far_, float near_) {
+    float v = (float)u;
+    if (u == 0u || (invalid && u == invalid)) v = far_;
+    if (v >= far_) v = far_;
+    if (v <= near_) v = near_;
+    return __fdiv_rn(__fsub_rn(v, cz), hz);
+}
+
+__global__ void __launch_bounds__(256)
+target_from_u16_kernel(int npix, const unsigned short* __restrict__ depth, const float* __restrict__ center,
+                       const float* __restrict__ cube, unsigned invalid, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float cz = center[3 * b + 2], hz = __fdiv_rn(cube[3 * b + 2], 2.f);
+    const float far_ = __fadd_rn(cz, hz), near_ = __fsub_rn(cz, hz);
+    const unsigned short* d = depth + (size_t)b * npix;
+    float* o = out + (size_t)b * npix;
+    const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (k + 8 <= npix && ((((size_t)b * npix) & 7) == 0)) {
+        const uint4 q = *reinterpret_cast<const uint4*>(d + k);
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[2 * i] = target_norm(w[i] & 0xffffu, invalid, cz, hz, far_, near_);
+            r[2 * i + 1] = target_norm(w[i] >> 16, invalid, cz, hz, far_, near_);
+        }
+        *reinterpret_cast<float4*>(o + k) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(o + k + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    } else {
+        for (int i = k; i < npix && i < k + 8; ++i) o[i] = target_norm(d[i], invalid, cz, hz, far_, near_);
+    }
+}
+
+extern "C" int dsf_target_from_u16(int batch, int R, const unsigned short* depth_mm, const float* center3d,
+                                   const float* cube, int invalid_value, float* target, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && R >= 2 && depth_mm && center3d && cube && target, "null / empty argument");
+    DSF_REQUIRE(invalid_value >= 0 && invalid_value <= 65535, "invalid_value must fit uint16 (0 = none)");
+    DSF_REQUIRE((((size_t)depth_mm) & 15) == 0 && (((size_t)target) & 15) == 0, "buffers must be 16-byte aligned");
+    const int npix = R * R;
+    dim3 grid((npix + 2047) / 2048, batch);
+    target_from_u16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(npix, depth_mm, center3d, cube, (unsigned)invalid_value,
+                                                                     target);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}

@@ -29,6 +29,7 @@ class FitStep:
         self.center3d = f(B, 3)
         self.cube = f(B, 3)
         self.target = f(B, R, R)
+        self.target_u16 = None            # allocated on first use (set_inputs with a uint16 target)
         self.view = f(B, L.VIEW_STRIDE)
         self.xs = f(B, R)
         self.ys = f(B, R)
@@ -63,7 +64,16 @@ class FitStep:
         self.center3d.copy_(center3d, non_blocking=True)
         self.cube.copy_(cube, non_blocking=True)
         if target is not None:
-            self.target.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
+            if target.dtype == torch.uint16:
+                # sensor format: uint16 millimetres travel over PCIe (half the bytes), normalised here
+                if self.target_u16 is None:
+                    self.target_u16 = torch.empty(self.B, self.R, self.R, dtype=torch.uint16, device=self.target.device)
+                self.target_u16.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
+                L.check(self.lib.dsf_target_from_u16(self.B, self.R, self.target_u16.data_ptr(),
+                                                     self.center3d.data_ptr(), self.cube.data_ptr(), 0,
+                                                     self.target.data_ptr(), L.stream_ptr()))
+            else:
+                self.target.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
 
     def set_crop_joints(self, joints):
         """Teacher joints (B,J,3) in normalised cube units: the rendered image is passed through

@@ -176,3 +176,16 @@ def sample_fit_inputs(batch: int, seed: int = 0, cube_mm: float = 250.0) -> dict
         "center3d": center.astype(np.float32),
         "cube": cube.astype(np.float32),
     }
+
+
+def quantise_depth_mm(img_norm, center3d, cube):
+    """Normalised depth crop (B,R,R) -> what a depth sensor would have delivered for it: integer
+    millimetres as uint16, 0 where there is no surface in the cube (background = 1.0).  Used by the
+    tests and the bench to make sensor-format targets from rendered images."""
+    import torch
+
+    B = img_norm.shape[0]
+    img = img_norm.reshape(B, -1)
+    d = img * (cube[:, 2:3] / 2.0) + center3d[:, 2:3]
+    mm = torch.where(img >= 0.99, torch.zeros_like(d), d.round().clamp(1, 65535))
+    return mm.to(torch.int32).to(torch.uint16).reshape(img_norm.shape)

@@ -211,6 +211,32 @@ int dsf_crop_hand(int batch, int R, const float* img, const float* joints, int n
                   float offset_xy, float offset_z, float thickness, float* out, unsigned char* keep,
                   dsfStream_t stream);
 
+/* "next" row f1 - replaces loader.Img2pcl (data/render_loader.py:1121-1156): nearest resize of the
+ * (B,R_in,R_in) normalised depth crop to feature_size^2, foreground = value <= 0.99, each foreground
+ * cell back-projected to cube-normalised xyz (uvd_nl2xyznl_tensor :1059-1073; M is inverted in the
+ * kernel, img_size / flip are loader.img_size / loader.flip), then a fixed-size cloud per hand:
+ * pcl (B, sample_num, 3) = [foreground list in pixel order, repeated floor(sample_num / n) times |
+ * sample_num mod n of them drawn without replacement, pixel order]; n = 0 gives zeros.  The draw is
+ * a counter-based hash of (seed, hand, pixel): uniform, reproducible, not torch.multinomial's stream.
+ * sample_num = 0: every foreground point in pixel order, pcl has feature_size^2 rows per hand of
+ * which the first count[b] are written.  count (B) int32 optional. */
+int dsf_img2pcl(int batch, int R_in, int feature_size, const float* img, const float* center3d,
+                const float* cube, const float* M, const float* intr4, float img_size, float flip,
+                int sample_num, unsigned long long seed, float* pcl, int* count, dsfStream_t stream);
+
+/* replaces loader.uvdImg2xyzImg (data/render_loader.py:1190-1200): per pixel camera-space xyz in mm
+ * and its cube-normalised copy, both (B,3,R,R); either output may be NULL. */
+int dsf_uvd_img_to_xyz(int batch, int R, const float* img, const float* center3d, const float* cube,
+                       const float* M, const float* intr4, float img_size, float flip, float* xyz_img,
+                       float* xyz_normal, dsfStream_t stream);
+
+/* data format either side of the path: the cropped sensor depth as uint16 millimetres (B,R,R)
+ * (0 = no reading; invalid_value, if non-zero, is the loader's `premax` marker) -> the normalised
+ * fp32 target (B,R,R) the m2d loss reads.  Replaces loader.normalize_img (data/render_loader.py:
+ * 738-745), which the reference runs on the CPU before a 4-byte-per-pixel upload. */
+int dsf_target_from_u16(int batch, int R, const unsigned short* depth_mm, const float* center3d,
+                        const float* cube, int invalid_value, float* target, dsfStream_t stream);
+
 /* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
 int dsf_last_launch_count(void);
 

@@ -318,3 +318,55 @@ def seg_pcl(c: ManoConstants, joints, joints_mano, mesh, pcl):
     pmin = pd.min(-1)[0]
     bone = (fid.float() / 3).long() + 1
     return torch.where(pmin < fmin, torch.zeros_like(bone), bone)
+
+
+# ----------------------------------------------------------------------------------------
+# "next" row f1 (second half): Img2pcl (data/render_loader.py:1121-1156) and uvdImg2xyzImg
+# (:1190-1200) with uvd_nl2xyznl_tensor / uvd_nl2xyz_tensor (:1044-1073).  M is inverted with
+# torch.inverse like the reference; flip = loader.flip, img_size = loader.img_size.
+# ----------------------------------------------------------------------------------------
+def uvd_img_to_xyz(img, center, M, cube, intr, img_size=None, flip=1.0):
+    """img (B,1,R,R) normalised depth -> (xyz_img mm, xyz_normal), both (B,3,R,R)."""
+    B, _, R, _ = img.shape
+    fx, fy, px, py = intr
+    img_size = float(R if img_size is None else img_size)
+    g = 2.0 * torch.arange(R, dtype=img.dtype) / (R - 1.0) - 1.0
+    uu = ((g + 1) * (img_size / 2)).view(1, 1, R).expand(B, R, R)
+    vv = ((g + 1) * (img_size / 2)).view(1, R, 1).expand(B, R, R)
+    d = img[:, 0] * (cube[:, 2] / 2.0).view(B, 1, 1) + center[:, 2].view(B, 1, 1)
+    Mi = torch.inverse(M)
+    us = Mi[:, 0, 0].view(B, 1, 1) * uu + Mi[:, 0, 1].view(B, 1, 1) * vv + Mi[:, 0, 2].view(B, 1, 1)
+    vs = Mi[:, 1, 0].view(B, 1, 1) * uu + Mi[:, 1, 1].view(B, 1, 1) * vv + Mi[:, 1, 2].view(B, 1, 1)
+    x = (us - px) * d / fx
+    y = flip * (vs - py) * d / fy
+    xyz = torch.stack([x, y, d], 1)
+    xyz_n = (xyz - center.view(B, 3, 1, 1)) / (cube.view(B, 3, 1, 1) / 2.0)
+    return xyz, xyz_n
+
+
+def img2pcl_points(img, feature_size, center, M, cube, intr, img_size=None, flip=1.0):
+    """The deterministic part of Img2pcl: per hand the (n_b,3) cube-normalised points of the
+    foreground cells (value <= 0.99) of the nearest-resized image, in pixel order."""
+    B, _, R, _ = img.shape
+    img_size = float(R if img_size is None else img_size)       # loader.img_size, NOT feature_size
+    img_rs = torch.nn.functional.interpolate(img, (feature_size, feature_size))
+    _, xyz_n = uvd_img_to_xyz(img_rs, center, M, cube, intr, img_size=img_size, flip=flip)
+    mask = img_rs[:, 0] <= 0.99
+    pts = xyz_n.permute(0, 2, 3, 1)
+    return [pts[b][mask[b]] for b in range(B)]
+
+
+def target_from_u16(depth_mm, center, cube, invalid_value=0):
+    """loader.normalize_img (data/render_loader.py:738-745) on a (B,R,R) integer-millimetre crop,
+    in float32 like the loader's arrays: invalid / zero / far -> far plane, near clamp, (d - cz) / (cube_z / 2)."""
+    d = depth_mm.to(torch.float32)
+    cz = center[:, 2].view(-1, 1, 1).to(torch.float32)
+    hz = (cube[:, 2] / 2.0).view(-1, 1, 1).to(torch.float32)
+    far, near = cz + hz, cz - hz
+    bad = depth_mm == 0
+    if invalid_value:
+        bad = bad | (depth_mm == invalid_value)
+    d = torch.where(bad, far.expand_as(d), d)
+    d = torch.where(d >= far, far.expand_as(d), d)
+    d = torch.where(d <= near, near.expand_as(d), d)
+    return (d - cz) / hz

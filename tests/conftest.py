@@ -20,6 +20,19 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def pcl_golden(golden):
+    """Img2pcl / uvdImg2xyzImg vectors (tests/golden/make_golden_pcl.py); the input image is the
+    crop_in of mano_golden.npz with hand 1 blanked, rebuilt here the way the generator does."""
+    import numpy as np
+
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "pcl_golden.npz")))
+    img = golden["crop_in"].copy()
+    img[1] = 1.0
+    g["img"] = img
+    return g
+
+
+@pytest.fixture(scope="session")
 def mano_model():
     from dsf_b200.synthetic import make_synthetic_mano
 

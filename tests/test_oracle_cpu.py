@@ -137,3 +137,66 @@ def test_seg_pcl_matches_reference(golden, mano_model):
     ref = torch.tensor(golden["seg_ref"]).long()
     assert len(ref.unique()) > 8, "golden case must hit many parts"
     assert (seg != ref).sum().item() == 0
+
+
+NYU_INTR = (588.03, 587.07, 320.0, 240.0)
+
+
+def _split(points, counts):
+    out, o = [], 0
+    for n in counts:
+        out.append(points[o:o + n])
+        o += n
+    return out
+
+
+def test_img2pcl_matches_reference_loader(pcl_golden):
+    """'next' row f1: the deterministic part of Img2pcl (foreground list in pixel order, back-projected
+    and cube-normalised) vs the reference loader's own output, incl. a rotated M, an empty crop and
+    the 128 -> 64 nearest resize."""
+    g = pcl_golden
+    img, center, cube, M = (torch.tensor(g[k]) for k in ("img", "center3d", "cube", "M"))
+    for fs in (128, 64):
+        mine = mo.img2pcl_points(img, fs, center, M, cube, NYU_INTR, img_size=128)
+        ref = _split(g[f"pts_{fs}"], g[f"cnt_{fs}"])
+        assert [len(m) for m in mine] == list(g[f"cnt_{fs}"])
+        for m, r in zip(mine, ref):
+            if len(r):
+                np.testing.assert_allclose(m.numpy(), r, rtol=1e-5, atol=2e-6)
+    assert g["cnt_128"][1] == 0 and (g["sampled_empty"] == 0).all()
+    # layout of the sampled mode (:1141-1153): [list repeated floor(S/n) times | S mod n distinct members]
+    n0 = int(g["cnt_128"][0])
+    s = g["sampled_3000"][0]
+    full = _split(g["pts_128"], g["cnt_128"])[0]
+    mult = 3000 // n0
+    assert mult == 2
+    np.testing.assert_array_equal(s[:mult * n0], np.tile(full, (mult, 1)))
+    rest = s[mult * n0:]
+    keys = {p.tobytes() for p in full}
+    assert all(p.tobytes() in keys for p in rest) and len({p.tobytes() for p in rest}) == len(rest)
+    for k, b in enumerate((0, 2)):                 # fewer samples than points: distinct members
+        s = g["sampled_2048"][k]
+        full = _split(g["pts_128"], g["cnt_128"])[b]
+        keys = {p.tobytes() for p in full}
+        if len(full) >= 2048:
+            assert all(p.tobytes() in keys for p in s) and len({p.tobytes() for p in s}) == 2048
+
+
+def test_uvd_img_to_xyz_matches_reference_loader(pcl_golden):
+    g = pcl_golden
+    img, center, cube, M = (torch.tensor(g[k]) for k in ("img", "center3d", "cube", "M"))
+    xyz, xyz_n = mo.uvd_img_to_xyz(img, center, M, cube, NYU_INTR, img_size=128)
+    B = img.shape[0]
+    np.testing.assert_allclose(xyz.reshape(B, 3, -1)[:, :, ::7].numpy(), g["xyz_sub"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(xyz_n.reshape(B, 3, -1)[:, :, ::7].numpy(), g["xyzn_sub"], rtol=1e-5, atol=2e-5)
+
+
+def test_target_from_u16_matches_reference_loader(pcl_golden):
+    """sensor-format target: the restated normalize_img (:738-745) is bit-identical to the loader's."""
+    g = pcl_golden
+    hands = g["u16_hands"]
+    mm = torch.from_numpy(g["u16_mm"].astype(np.int32))
+    out = mo.target_from_u16(mm, torch.tensor(g["center3d"])[hands], torch.tensor(g["cube"])[hands],
+                             invalid_value=int(g["u16_premax"]))
+    assert (g["u16_norm"] == 1.0).sum() > 100 and (np.abs(g["u16_norm"]) < 0.9).sum() > 100
+    np.testing.assert_array_equal(out.numpy(), g["u16_norm"])
