@@ -237,6 +237,24 @@ int dsf_uvd_img_to_xyz(int batch, int R, const float* img, const float* center3d
 int dsf_target_from_u16(int batch, int R, const unsigned short* depth_mm, const float* center3d,
                         const float* cube, int invalid_value, float* target, dsfStream_t stream);
 
+/* I1 - replaces eval_coll.py:611-626 self_intersection (with get_part_mesh :348-373) and
+ * util/intersect.py:102-107 intersect_vox, i.e. trimesh's voxelized(pitch).points +
+ * mesh.contains(points) on the CPU.  verts (B,n_verts,3) fp32 (mm); cap centre c = mean of the
+ * vertices cap_idx[cap_ptr[c] .. cap_ptr[c+1]) and becomes water vertex n_verts + c; part p owns the
+ * triangles part_faces[part_ptr[p] .. part_ptr[p+1]) (int32 triples into the water mesh, watertight);
+ * pair_mask[s*n_parts+t] != 0: count the surface voxels of t whose centre lies inside s.
+ * Outputs: pair_counts (B,n_parts,n_parts) int64, voxel_counts (B,n_parts) int64 or NULL,
+ * volume (B) float64 = sum(pair_counts) * pitch^3 (-1 if status != 0), status (B) int32 bit 0 = a
+ * one z-layer of a part exceeds the voxel bitmap (1.5 M voxels; larger boxes are processed in z-slabs), bit 1 = more than 10 subdivision levels
+ * (trimesh raises there).  All topology arrays and outputs are device pointers; workspace of
+ * dsf_intersect_workspace_bytes() bytes, 8-byte aligned.  Geometry is evaluated in float64. */
+long dsf_intersect_workspace_bytes(int batch, int n_verts, int n_caps, int n_parts);
+int dsf_intersect_vox(int batch, int n_verts, const float* verts, int n_caps, const int* cap_ptr,
+                      const int* cap_idx, int n_parts, const int* part_ptr, const int* part_faces,
+                      const unsigned char* pair_mask, double pitch, long long* pair_counts,
+                      long long* voxel_counts, double* volume, int* status, void* workspace,
+                      dsfStream_t stream);
+
 /* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
 int dsf_last_launch_count(void);
 

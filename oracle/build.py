@@ -4,7 +4,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "liboracle_dsf.so")
-SRCS = ["raster_oracle.c", "raster_oracle_impl.h", "pointface_oracle_impl.h"]
+SRCS = ["raster_oracle.c", "raster_oracle_impl.h", "pointface_oracle_impl.h", "intersect_oracle.c"]
+UNITS = ["raster_oracle.c", "intersect_oracle.c"]
 
 
 def build(force: bool = False) -> str:
@@ -13,7 +14,7 @@ def build(force: bool = False) -> str:
             and os.path.getmtime(SO) >= max(os.path.getmtime(s) for s in srcs)):
         return SO
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
-           "-o", SO, srcs[0], "-lm"]
+           "-o", SO] + [os.path.join(HERE, u) for u in UNITS] + ["-lm"]
     subprocess.check_call(cmd)
     return SO
 
