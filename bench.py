@@ -397,6 +397,25 @@ def run_ours(args):
                                      "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
                                      "note": "brute-force ICPLoss fwd+bwd; FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
+        # "next" rows: depth crop -> 2048-point cloud (Img2pcl) and the intersection-volume metric (I1)
+        from dsf_b200.intersection import PartTopology, intersect_counts
+        from dsf_b200.pcl import Img2pcl
+        s2.step()
+        t_pcl = time_region(lambda: Img2pcl(s2.img, CROP, s2.center3d, s2.M, s2.cube, 2048, seed=1), 50)
+        other["img2pcl_batch1024"] = {"hands": 1024, "points": 2048, "ms": t_pcl, "hands_per_s": 1024 / (t_pcl * 1e-3),
+                                      "GB_per_s": 1024 * (CROP * CROP * 4 + 2048 * 12) / (t_pcl * 1e-3) / 1e9}
+        topo = PartTopology.synthetic_hand()
+        v_mm = layer.get_mano_vertices(p4[:256, :3], p4[:256, 3:48] * 3, p4[:256, 48:58], p4[:256, 58:])[0].detach()
+        intersect_counts(v_mm, topo, 2.0)
+        t_iv = time_region(lambda: intersect_counts(v_mm, topo, 2.0), 5)
+        from oracle import intersect_oracle as io
+        t0 = time.perf_counter()
+        io.intersect_vox(v_mm[:32].cpu().numpy(), topo, 2.0)
+        t_iv_cpu = time.perf_counter() - t0
+        other["I1_intersection_volume_batch256"] = {
+            "hands": 256, "pitch_mm": 2.0, "ms": t_iv, "hands_per_s": 256 / (t_iv * 1e-3),
+            "cpu_oracle_hands_per_s": 32 / t_iv_cpu, "cpu_cores": os.cpu_count(),
+            "note": "15 watertight parts, 91 pairs, curled synthetic hands; float64 ray parity"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cstep, cores = cpu_pipeline(args.ref_batch)
