@@ -352,8 +352,11 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 #define RT_THREADS 512
 #define RT_MAXR 512
 #define RT_CAP 4096          // (items + candidates) / 2: list storage in 32-bit entries
+#ifndef RT_V2
+#define RT_V2 1              // 1: closed-form row runs (no item list, no per-pixel pre-test); 0: the three-phase v1
+#endif
 #ifndef RT_WITEMS
-#define RT_WITEMS 128        // per-warp item list      (16 warps x 128 = 2048 entries)
+#define RT_WITEMS (RT_V2 ? 0 : 128)   // per-warp item list (v1 only)
 #endif
 #define RT_WCANDS (512 - RT_WITEMS)   // per-warp candidate list (16 warps x 512 entries in total)
 #ifndef RT_SEG
@@ -439,6 +442,48 @@ __device__ __forceinline__ unsigned int segment_hits(const RasterSmem& s, unsign
         }
     }
     return hits;
+}
+
+// Conservative pixel run of face f on row j: every pixel of [ia,ib] that the exact edge-sign test
+// (segment_hits / the oracle's strict-inside rule) can accept lies in the returned [ka,kb].
+// The three edge functions are linear in px, e_i(px) = (px - xa_i) * dy_i - r_i with the oracle's own
+// rounded constants, and for a face of orientation s = sign(area) the accepted pixels satisfy
+// s * e_i > 0, i.e. px beyond / before the crossing c_i = xa_i + r_i / dy_i.  The float evaluation
+// of e_i can disagree with the real sign only within 2.1 u |px - xa_i| of c_i (u = 2^-24) and c_i is
+// computed here to a few ulp, so the bounds are widened by 2e-6 (1 + |xa_i| + |c_i - xa_i|): about
+// 1e-4 of a pixel at R = 128, never a missed pixel.  Slivers (|area| < 1e-5, where float edge signs
+// need not be consistent with the orientation) keep the whole bbox row.  Phase C re-tests exactly.
+__device__ __forceinline__ void row_run(const RasterSmem& s, const ViewRec& vw, unsigned int f, int j, int ia, int ib,
+                                        int* ka_out, int* kb_out) {
+    const unsigned int pk = s.fp[f];
+    const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+    const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
+    const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
+    const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
+    int ka = ia, kb = ib;
+    const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
+    if (fabsf(farea) >= 1e-5f) {
+        const float py = s.ys[j];
+        const float sg = farea > 0.f ? 1.f : -1.f;
+        float lo = -INFINITY, hi = INFINITY;
+        auto clip = [&](float xa, float dy, float r) {
+            const float q = __fdividef(r, dy);
+            if (fabsf(q) < 1e30f) {                       // near-horizontal edge: no constraint (conservative)
+                const float c = xa + q;
+                const float dl = 2e-6f * (1.f + fabsf(xa) + fabsf(q));
+                if (sg * dy > 0.f) lo = fmaxf(lo, c - dl);
+                else hi = fminf(hi, c + dl);
+            }
+        };
+        clip(x1, __fsub_rn(y2, y1), __fmul_rn(__fsub_rn(py, y1), __fsub_rn(x2, x1)));
+        clip(x2, __fsub_rn(y0, y2), __fmul_rn(__fsub_rn(py, y2), __fsub_rn(x0, x2)));
+        clip(x0, __fsub_rn(y1, y0), __fmul_rn(__fsub_rn(py, y0), __fsub_rn(x1, x0)));
+        // xs is non-increasing: large x = small index
+        if (hi < INFINITY) ka = max(ia, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, hi));
+        if (lo > -INFINITY) kb = min(ib, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, lo));
+    }
+    *ka_out = ka;
+    *kb_out = kb;
 }
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
@@ -544,7 +589,9 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     // own private lists (warp-level synchronisation only), so no CTA barrier separates the phases
     // and a slow batch never stalls the other warps; the z-buffer is shared through atomicMin.
     const int warp = tid >> 5;
+#if !RT_V2
     unsigned int* my_items = s.items + warp * RT_WITEMS;
+#endif
     unsigned int* my_cands = s.cands + warp * RT_WCANDS;
     int n_cands = 0;
     auto flush_cands = [&]() {
@@ -556,6 +603,78 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         n_cands = 0;
         __syncwarp();
     };
+#if RT_V2
+    // v2: no item list and no per-pixel pre-test.  Phase A (lane / face) yields the clipped pixel bbox;
+    // the batch's bbox rows are then dealt out one per lane (owner found by a shuffle binary search over
+    // the prefix sums), each lane solves its row's pixel run in closed form (row_run) and appends the
+    // run's pixels to the warp's candidate list; phase C evaluates candidates exactly, 32 at a time.
+    while (tile_live) {
+        int fb = 0;
+        if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
+        fb = __shfl_sync(0xffffffffu, fb, 0);
+        if (fb >= F) break;
+        const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
+        int ia = 0, ib = -1, ja = 0, jb = -1;
+        if (f < F) {
+            const unsigned int pk = s.fp[f];
+            const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
+            const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1], z0 = s.vn[3 * a0 + 2];
+            const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1], z1 = s.vn[3 * a1 + 2];
+            const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
+            const float zmin = fminf(z0, fminf(z1, z2));
+            const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
+            if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
+                const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
+                const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
+                ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
+                jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
+                if (ja <= jb) {
+                    ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
+                    ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
+                }
+            }
+        }
+        const int n = (ib >= ia && jb >= ja) ? jb - ja + 1 : 0;
+        const unsigned int own = (unsigned int)f | ((unsigned int)(ia - tx0) << 11) | ((unsigned int)(ib - tx0) << 18) |
+                                 ((unsigned int)(ja - ty0) << 25);
+        int total;
+        const int excl = warp_excl_scan(n, lane, &total);
+        const int incl = excl + n;
+        for (int it0 = 0; it0 < total; it0 += 32) {
+            const int t = it0 + lane;
+            // owner = number of lanes whose inclusive prefix is <= t
+            int ow = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, ow + step - 1);
+                if (v <= t) ow += step;
+            }
+            const bool live = t < total;
+            ow = live ? ow : 0;
+            const unsigned int o_pk = __shfl_sync(0xffffffffu, own, ow);
+            const int o_ex = __shfl_sync(0xffffffffu, excl, ow);
+            int ka = 0, kb = -1, j = 0;
+            const unsigned int fi = o_pk & 2047u;
+            if (live) {
+                j = ty0 + (int)(o_pk >> 25) + (t - o_ex);
+                row_run(s, vw, fi, j, tx0 + (int)((o_pk >> 11) & 127u), tx0 + (int)((o_pk >> 18) & 127u), &ka, &kb);
+            }
+            const int len = max(0, kb - ka + 1);
+            int c_total;
+            int slot = warp_excl_scan(len, lane, &c_total);
+            if (n_cands + c_total > RT_WCANDS) flush_cands();
+            if (c_total > RT_WCANDS) {                           // very large faces: evaluate in place
+                for (int k = ka; k <= kb; ++k) eval_and_commit(s, fi, k, j, tx0, ty0);
+                __syncwarp();
+                continue;
+            }
+            slot += n_cands;
+            const unsigned int base = fi | ((unsigned int)(j - ty0) << 11);
+            for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
+            n_cands += c_total;
+        }
+    }
+#else
     while (tile_live) {
         int fb = 0;
         if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
@@ -628,6 +747,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             __syncwarp();
         }
     }
+#endif
     flush_cands();                                            // ---------------- phase C (remainder)
     __syncthreads();
 
@@ -644,6 +764,48 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         if (tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
         __syncthreads();
     }
+    const bool fast = !zbuf && !bary && !dists && (R & 3) == 0 && (tw & 3) == 0;
+    if (fast) {
+        // default outputs only: four pixels per lane, 128-bit key / target loads and image stores;
+        // background pixels (most of the image) take the precomputed normalised far plane
+        const float bgval = __fdiv_rn(__fsub_rn(zmax, vw.zc), vw.zh);
+        const int qw = tw >> 2;
+        for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
+            for (int q4 = lane; q4 < qw; q4 += 32) {
+                const int lx = q4 * 4;
+                const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
+                float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (target) tg = __ldg(reinterpret_cast<const float4*>(target + o));
+                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
+                const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
+                const unsigned long long kk[4] = {k01.x, k01.y, k23.x, k23.y};
+                const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
+                float v[4];
+                int ff[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (kk[c] == ~0ull) {
+                        v[c] = bgval;
+                        ff[c] = -1;
+                    } else {
+                        const float z = __uint_as_float((unsigned int)(kk[c] >> 32));
+                        float d = z <= 0.f ? 0.f : z;
+                        d = (d == 0.f) ? zmax : d;
+                        d = d > zmax ? zmax : d;
+                        d = d < zmin_c ? zmin_c : d;
+                        v[c] = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
+                        ff[c] = (int)(unsigned int)(kk[c] & 0xffffffffu);
+                    }
+                    if (target) {
+                        const float vc = (do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh)) ? 1.f : v[c];
+                        if (tt[c] < thr || vc < thr) { l_sum += fabsf(tt[c] - vc); l_cnt += 1.f; }
+                    }
+                }
+                *reinterpret_cast<float4*>(img + o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<int4*>(p2f + o) = make_int4(ff[0], ff[1], ff[2], ff[3]);
+            }
+        }
+    } else
     for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
         // all target loads of the row are issued before any of them is consumed
         float tg[RT_TW / 32];
