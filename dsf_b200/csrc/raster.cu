@@ -95,6 +95,7 @@ __global__ void view_setup_kernel(int mode, int B, const float* __restrict__ cen
             vw[7] = -half; vw[8] = ((float)R - 1.f) * 0.5f;
             vw[9] = -half; vw[10] = ((float)R - 1.f) * 0.5f;
             vw[11] = 0.f; vw[12] = (float)(R - 1); vw[13] = 0.f; vw[14] = (float)(R - 1);
+            vw[15] = 1.f;      // the sample grid is affine: index = a * ndc + b exactly (a, b above)
         } else {
             float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
             vw[0] = __fdiv_rn(fx, hw);
@@ -164,6 +165,7 @@ extern "C" int dsf_view_setup(int mode, int batch, const float* center3d, const 
 struct ViewRec {
     float fxn, fyn, pxn, pyn, zc, zh, bg, ax, bx, ay, by;
     int xlo, xhi, ylo, yhi;
+    bool affine;
 };
 
 __device__ __forceinline__ ViewRec load_view(const float* v) {
@@ -171,6 +173,7 @@ __device__ __forceinline__ ViewRec load_view(const float* v) {
     r.fxn = v[0]; r.fyn = v[1]; r.pxn = v[2]; r.pyn = v[3]; r.zc = v[4]; r.zh = v[5]; r.bg = v[6];
     r.ax = v[7]; r.bx = v[8]; r.ay = v[9]; r.by = v[10];
     r.xlo = (int)v[11]; r.xhi = (int)v[12]; r.ylo = (int)v[13]; r.yhi = (int)v[14];
+    r.affine = v[15] != 0.f;
     return r;
 }
 
@@ -341,27 +344,21 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 // ------------------------------------------------------------------------------------------------
 // forward: grid (tiles, meshes); one CTA owns a 128 x 64 pixel tile of one mesh (half the image at
 // R = 128) with its z-buffer in shared memory as packed 64-bit (depth bits << 32 | face) keys.
-// Work is re-balanced twice through shared-memory lists so that lanes stay busy:
-//   phase A  thread per face   : cull, exact pixel bbox, emit one item per (row, <= 8 pixel segment)
-//   phase B  thread per item   : exact edge-sign pre-test of the segment's pixels, emit candidates
-//   phase C  thread per cand.  : full oracle-order fragment evaluation + atomicMin on the key
-// List overflow falls back to evaluating in place, so any mesh / crop size is handled.
+// Each warp pulls batches of 32 faces and keeps its lanes busy through two re-balancing steps:
+//   phase A  lane per face      : cull, exact clipped pixel bbox -> number of rows
+//   phase B  lane per (face,row): rows dealt out by a shuffle binary search over the prefix sums; the
+//                                 row's pixel run is solved in closed form from the three edge
+//                                 crossings (conservative by ~1e-4 px) and appended to a warp-private
+//                                 candidate list in shared memory
+//   phase C  lane per candidate : full oracle-order fragment evaluation + early z + atomicMin on the key
+// A batch whose runs exceed the list is evaluated in place, so any mesh / crop size is handled.
 // ------------------------------------------------------------------------------------------------
 #define RT_TW 128            // tile width  (pixels)
 #define RT_TH 64             // tile height: 64 KB of keys -> two CTAs per SM
 #define RT_THREADS 512
 #define RT_MAXR 512
 #define RT_CAP 4096          // (items + candidates) / 2: list storage in 32-bit entries
-#ifndef RT_V2
-#define RT_V2 1              // 1: closed-form row runs (no item list, no per-pixel pre-test); 0: the three-phase v1
-#endif
-#ifndef RT_WITEMS
-#define RT_WITEMS (RT_V2 ? 0 : 128)   // per-warp item list (v1 only)
-#endif
-#define RT_WCANDS (512 - RT_WITEMS)   // per-warp candidate list (16 warps x 512 entries in total)
-#ifndef RT_SEG
-#define RT_SEG 8
-#endif
+#define RT_WCANDS 512        // per-warp candidate list (16 warps x 512 entries = 2 * RT_CAP)
 #define RT_MAXF 2047         // face id is packed into 11 bits
 
 struct RasterSmem {
@@ -383,7 +380,7 @@ __device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int 
     s.ys = s.xs + R;
     s.fp = reinterpret_cast<unsigned int*>(s.ys + R);
     s.items = s.fp + ((F + 3) & ~3);
-    s.cands = s.items + (RT_THREADS / 32) * RT_WITEMS;
+    s.cands = s.items;
     s.counters = reinterpret_cast<int*>(s.items + 2 * RT_CAP);
     return s;
 }
@@ -414,38 +411,8 @@ __device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned in
     atomicMin(slot, ((unsigned long long)__float_as_uint(pz) << 32) | f);
 }
 
-// pre-test of one row segment: bit k of the result = pixel i0+k passes the edge-sign test
-__device__ __forceinline__ unsigned int segment_hits(const RasterSmem& s, unsigned int f, int i0, int len, int j) {
-    const unsigned int pk = s.fp[f];
-    const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
-    const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
-    const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
-    const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
-    const float py = s.ys[j];
-    // edge deltas: the same single roundings the oracle performs inline
-    const float d0y = __fsub_rn(y2, y1), d1y = __fsub_rn(y0, y2), d2y = __fsub_rn(y1, y0);
-    const float r0 = __fmul_rn(__fsub_rn(py, y1), __fsub_rn(x2, x1));
-    const float r1 = __fmul_rn(__fsub_rn(py, y2), __fsub_rn(x0, x2));
-    const float r2 = __fmul_rn(__fsub_rn(py, y0), __fsub_rn(x1, x0));
-    unsigned int hits = 0;
-#pragma unroll
-    for (int k = 0; k < RT_SEG; ++k) {
-        if (k < len) {
-            const float px = s.xs[i0 + k];
-            const float e0 = __fsub_rn(__fmul_rn(__fsub_rn(px, x1), d0y), r0);
-            const float e1 = __fsub_rn(__fmul_rn(__fsub_rn(px, x2), d1y), r1);
-            const float e2 = __fsub_rn(__fmul_rn(__fsub_rn(px, x0), d2y), r2);
-            // all three barycentrics share the sign of e_i / area; mixed signs can never be inside
-            const bool pos = e0 > 0.f && e1 > 0.f && e2 > 0.f;
-            const bool neg = e0 < 0.f && e1 < 0.f && e2 < 0.f;
-            if (pos || neg) hits |= 1u << k;
-        }
-    }
-    return hits;
-}
-
 // Conservative pixel run of face f on row j: every pixel of [ia,ib] that the exact edge-sign test
-// (segment_hits / the oracle's strict-inside rule) can accept lies in the returned [ka,kb].
+// (all three oracle-order edge functions strictly of one sign) can accept lies in the returned [ka,kb].
 // The three edge functions are linear in px, e_i(px) = (px - xa_i) * dy_i - r_i with the oracle's own
 // rounded constants, and for a face of orientation s = sign(area) the accepted pixels satisfy
 // s * e_i > 0, i.e. px beyond / before the crossing c_i = xa_i + r_i / dy_i.  The float evaluation
@@ -479,8 +446,15 @@ __device__ __forceinline__ void row_run(const RasterSmem& s, const ViewRec& vw, 
         clip(x2, __fsub_rn(y0, y2), __fmul_rn(__fsub_rn(py, y2), __fsub_rn(x0, x2)));
         clip(x0, __fsub_rn(y1, y0), __fmul_rn(__fsub_rn(py, y0), __fsub_rn(x1, x0)));
         // xs is non-increasing: large x = small index
-        if (hi < INFINITY) ka = max(ia, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, hi));
-        if (lo > -INFINITY) kb = min(ib, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, lo));
+        if (vw.affine) {
+            // direct mode: index = ax * x + bx exactly, so x <= hi <=> index >= ax * hi + bx; a thousandth
+            // of a pixel of slack covers the rounding of the map (infinite bounds saturate to the bbox)
+            ka = max(ia, (int)ceilf(fmaf(vw.ax, hi, vw.bx) - 1e-3f));
+            kb = min(ib, (int)floorf(fmaf(vw.ax, lo, vw.bx) + 1e-3f));
+        } else {
+            if (hi < INFINITY) ka = max(ia, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, hi));
+            if (lo > -INFINITY) kb = min(ib, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, lo));
+        }
     }
     *ka_out = ka;
     *kb_out = kb;
@@ -589,9 +563,6 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     // own private lists (warp-level synchronisation only), so no CTA barrier separates the phases
     // and a slow batch never stalls the other warps; the z-buffer is shared through atomicMin.
     const int warp = tid >> 5;
-#if !RT_V2
-    unsigned int* my_items = s.items + warp * RT_WITEMS;
-#endif
     unsigned int* my_cands = s.cands + warp * RT_WCANDS;
     int n_cands = 0;
     auto flush_cands = [&]() {
@@ -603,40 +574,11 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         n_cands = 0;
         __syncwarp();
     };
-#if RT_V2
-    // v2: no item list and no per-pixel pre-test.  Phase A (lane / face) yields the clipped pixel bbox;
+    // no item list and no per-pixel pre-test.  Phase A (lane / face) yields the clipped pixel bbox;
     // the batch's bbox rows are then dealt out one per lane (owner found by a shuffle binary search over
     // the prefix sums), each lane solves its row's pixel run in closed form (row_run) and appends the
     // run's pixels to the warp's candidate list; phase C evaluates candidates exactly, 32 at a time.
-    while (tile_live) {
-        int fb = 0;
-        if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
-        fb = __shfl_sync(0xffffffffu, fb, 0);
-        if (fb >= F) break;
-        const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
-        int ia = 0, ib = -1, ja = 0, jb = -1;
-        if (f < F) {
-            const unsigned int pk = s.fp[f];
-            const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
-            const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1], z0 = s.vn[3 * a0 + 2];
-            const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1], z1 = s.vn[3 * a1 + 2];
-            const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
-            const float zmin = fminf(z0, fminf(z1, z2));
-            const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
-            if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
-                const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
-                const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
-                ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
-                jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
-                if (ja <= jb) {
-                    ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
-                    ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
-                }
-            }
-        }
-        const int n = (ib >= ia && jb >= ja) ? jb - ja + 1 : 0;
-        const unsigned int own = (unsigned int)f | ((unsigned int)(ia - tx0) << 11) | ((unsigned int)(ib - tx0) << 18) |
-                                 ((unsigned int)(ja - ty0) << 25);
+    auto sweep_rows = [&](unsigned int own, int n) {
         int total;
         const int excl = warp_excl_scan(n, lane, &total);
         const int incl = excl + n;
@@ -673,16 +615,12 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
             n_cands += c_total;
         }
-    }
-#else
+    };
     while (tile_live) {
         int fb = 0;
         if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
         fb = __shfl_sync(0xffffffffu, fb, 0);
         if (fb >= F) break;
-        // ---------------- phase A: 32 faces -> row-segment items ----------------
-        // batches follow face_order (largest rest-pose area first) so the expensive batches are
-        // handed out early and the warps drain together before the epilogue barrier
         const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
         int ia = 0, ib = -1, ja = 0, jb = -1;
         if (f < F) {
@@ -693,11 +631,9 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1], z2 = s.vn[3 * a2 + 2];
             const float zmin = fminf(z0, fminf(z1, z2));
             const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
-            // behind / at the camera, or degenerate in NDC
             if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
                 const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
                 const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
-                // rows first: tiles split the image in y, so half the faces drop out here
                 ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
                 jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
                 if (ja <= jb) {
@@ -706,48 +642,11 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                 }
             }
         }
-        const int w = ib - ia + 1, hgt = jb - ja + 1;
-        const int nseg = (w + RT_SEG - 1) / RT_SEG;
-        const int n = (w > 0 && hgt > 0) ? nseg * hgt : 0;
-        int total;
-        const int excl = warp_excl_scan(n, lane, &total);
-        for (int w0 = 0; w0 < total; w0 += RT_WITEMS) {          // windows of the batch's item sequence
-            const int k_lo = max(0, w0 - excl), k_hi = min(n, w0 + RT_WITEMS - excl);
-            for (int k = k_lo; k < k_hi; ++k) {
-                const int row = nseg == 1 ? k : k / nseg;
-                const int i0 = ia + (k - row * nseg) * RT_SEG;
-                const int len = min(RT_SEG, ib - i0 + 1);
-                my_items[excl + k - w0] = (unsigned int)f | ((unsigned int)(ja + row - ty0) << 11) |
-                                          ((unsigned int)(i0 - tx0) << 18) | ((unsigned int)(len - 1) << 25);
-            }
-            __syncwarp();
-            // ---------------- phase B: items -> candidates ----------------
-            const int n_items = min(RT_WITEMS, total - w0);
-            for (int it0 = 0; it0 < n_items; it0 += 32) {
-                if (n_cands > RT_WCANDS - 32 * RT_SEG) flush_cands();      // phase C when the list may overflow
-                const int it = it0 + lane;
-                unsigned int hits = 0, fi = 0;
-                int i0 = 0, j = 0;
-                if (it < n_items) {
-                    const unsigned int e = my_items[it];
-                    fi = e & 2047u;
-                    j = ty0 + (int)((e >> 11) & 127u);
-                    i0 = tx0 + (int)((e >> 18) & 127u);
-                    hits = segment_hits(s, fi, i0, (int)((e >> 25) & 7u) + 1, j);
-                }
-                int c_total;
-                int slot = n_cands + warp_excl_scan(__popc(hits), lane, &c_total);
-                while (hits) {
-                    const int k = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    my_cands[slot++] = fi | ((unsigned int)(j - ty0) << 11) | ((unsigned int)(i0 + k - tx0) << 18);
-                }
-                n_cands += c_total;
-            }
-            __syncwarp();
-        }
+        const int n = (ib >= ia && jb >= ja) ? jb - ja + 1 : 0;
+        const unsigned int own = (unsigned int)f | ((unsigned int)(ia - tx0) << 11) | ((unsigned int)(ib - tx0) << 18) |
+                                 ((unsigned int)(ja - ty0) << 25);
+        sweep_rows(own, n);
     }
-#endif
     flush_cands();                                            // ---------------- phase C (remainder)
     __syncthreads();
 
@@ -951,7 +850,8 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     // NB float atomicAdd on shared memory is a compare-and-swap loop on this architecture (SASS
     // ATOMS.CAST.SPIN); accumulating with native global reductions (RED.E.ADD.F32 into the output
     // rows) was measured 1.9x slower (L2 atomic throughput), so the accumulator stays in shared
-    // memory and the per-face warp reduction below keeps the number of atomics small.
+    // memory and the per-face warp reduction below keeps the number of atomics small.  (One 128-bit
+    // CAS per vertex, ATOMS.CAS.128, instead of three 32-bit loops was measured 1.4x slower.)
     const ViewRec vw = load_view(view + (size_t)mesh * VIEW);
     for (int i = tid; i < R; i += RB_THREADS) {
         sxs[i] = xs_g[(size_t)mesh * R + i];
