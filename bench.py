@@ -205,6 +205,15 @@ def stage_times(step, iters=10):
     for name, fn in stages.items():
         fn()
         out[name] = time_region(fn, iters)
+    # Fragments-materialising mode (SURVEY 8d accounting F): the rasteriser also writes the barycentrics
+    # (3 x fp32 per pixel) next to depth and pix_to_face - the full "z-buffer + pix_to_face + barycentrics"
+    # product of north_star piece (2).  Bytes really moved: 20 B/pixel out + the mesh in.
+    bary = torch.empty(B, R, R, 3, device=step.dev)
+    frag = lambda: L.check(lib.dsf_raster_forward(
+        h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
+        step.img.data_ptr(), step.p2f.data_ptr(), None, bary.data_ptr(), None, None, 0.99, None, s))
+    frag()
+    out["raster_fwd_kernel[fragments mode: +barycentrics]"] = time_region(frag, iters)
     return out
 
 
@@ -335,6 +344,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel, timed live with CUDA events ----
     peak, peak_src = measured_peaks()
     st = stage_times(step)
+    frag_key = "raster_fwd_kernel[fragments mode: +barycentrics]"
+    frag_ms = st.pop(frag_key)
     dom = max(st, key=st.get)
     dom_ms = st["raster_fwd_kernel"]
     traffic = None
@@ -354,6 +365,11 @@ def run_ours(args):
         "stage_ms": st, "slowest_stage": dom,
         "step": {"bytes_per_fit": BYTES_PER_FIT, "achieved": step_gbs, "frac": step_gbs / peak},
     }
+    frag_bytes = (779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 5 * CROP * CROP * 4) * B
+    roofline["fragments_mode"] = {
+        "what": "same kernel also writing barycentrics (3 x fp32 / pixel): depth + pix_to_face + bary out, mesh in; no loss fusion",
+        "kernel_ms": frag_ms, "bytes_per_launch": frag_bytes, "achieved": frag_bytes / (frag_ms * 1e-3) / 1e9,
+        "frac": frag_bytes / (frag_ms * 1e-3) / 1e9 / peak}
     other = {}
     if world == 1 and not args.no_other_configs:
         for name, b2 in (("C1_batch128", 128), ("batch1024", 1024)):
@@ -364,7 +380,9 @@ def run_ours(args):
             for _ in range(5):
                 s2.step()
             t2 = time_region(s2.step, 200)
+            st2 = stage_times(s2, iters=50)
             other[name] = {"hands": b2, "ms_per_step": t2, "fits_per_s": b2 / (t2 * 1e-3),
+                           "stage_ms": {k: round(v, 4) for k, v in st2.items()},
                            "step_hbm_frac": BYTES_PER_FIT * b2 / (t2 * 1e-3) / 1e9 / peak,
                            "note": "inputs fit in L2 at this size (no flush): latency/launch-bound regime"}
         # config C4 (BASELINE.json configs[4]): self-penetration + point-to-mesh terms, batch 1024

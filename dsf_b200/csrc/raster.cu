@@ -411,55 +411,16 @@ __device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned in
     atomicMin(slot, ((unsigned long long)__float_as_uint(pz) << 32) | f);
 }
 
-// Conservative pixel run of face f on row j: every pixel of [ia,ib] that the exact edge-sign test
-// (all three oracle-order edge functions strictly of one sign) can accept lies in the returned [ka,kb].
-// The three edge functions are linear in px, e_i(px) = (px - xa_i) * dy_i - r_i with the oracle's own
-// rounded constants, and for a face of orientation s = sign(area) the accepted pixels satisfy
-// s * e_i > 0, i.e. px beyond / before the crossing c_i = xa_i + r_i / dy_i.  The float evaluation
-// of e_i can disagree with the real sign only within 2.1 u |px - xa_i| of c_i (u = 2^-24) and c_i is
-// computed here to a few ulp, so the bounds are widened by 2e-6 (1 + |xa_i| + |c_i - xa_i|): about
-// 1e-4 of a pixel at R = 128, never a missed pixel.  Slivers (|area| < 1e-5, where float edge signs
-// need not be consistent with the orientation) keep the whole bbox row.  Phase C re-tests exactly.
-__device__ __forceinline__ void row_run(const RasterSmem& s, const ViewRec& vw, unsigned int f, int j, int ia, int ib,
-                                        int* ka_out, int* kb_out) {
-    const unsigned int pk = s.fp[f];
-    const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
-    const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
-    const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
-    const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
-    int ka = ia, kb = ib;
-    const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
-    if (fabsf(farea) >= 1e-5f) {
-        const float py = s.ys[j];
-        const float sg = farea > 0.f ? 1.f : -1.f;
-        float lo = -INFINITY, hi = INFINITY;
-        auto clip = [&](float xa, float dy, float r) {
-            const float q = __fdividef(r, dy);
-            if (fabsf(q) < 1e30f) {                       // near-horizontal edge: no constraint (conservative)
-                const float c = xa + q;
-                const float dl = 2e-6f * (1.f + fabsf(xa) + fabsf(q));
-                if (sg * dy > 0.f) lo = fmaxf(lo, c - dl);
-                else hi = fminf(hi, c + dl);
-            }
-        };
-        clip(x1, __fsub_rn(y2, y1), __fmul_rn(__fsub_rn(py, y1), __fsub_rn(x2, x1)));
-        clip(x2, __fsub_rn(y0, y2), __fmul_rn(__fsub_rn(py, y2), __fsub_rn(x0, x2)));
-        clip(x0, __fsub_rn(y1, y0), __fmul_rn(__fsub_rn(py, y0), __fsub_rn(x1, x0)));
-        // xs is non-increasing: large x = small index
-        if (vw.affine) {
-            // direct mode: index = ax * x + bx exactly, so x <= hi <=> index >= ax * hi + bx; a thousandth
-            // of a pixel of slack covers the rounding of the map (infinite bounds saturate to the bbox)
-            ka = max(ia, (int)ceilf(fmaf(vw.ax, hi, vw.bx) - 1e-3f));
-            kb = min(ib, (int)floorf(fmaf(vw.ax, lo, vw.bx) + 1e-3f));
-        } else {
-            if (hi < INFINITY) ka = max(ia, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, hi));
-            if (lo > -INFINITY) kb = min(ib, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, lo));
-        }
-    }
-    *ka_out = ka;
-    *kb_out = kb;
-}
-
+// Conservative pixel runs (phase B of the forward kernel).  The three edge functions of a face are linear
+// in px, e_i(px) = (px - xa_i) * dy_i - r_i with the oracle's own rounded constants, and for a face of
+// orientation s = sign(area) the accepted pixels (all three oracle-order edge functions strictly of one
+// sign) satisfy s * e_i > 0, i.e. px beyond / before the crossing c_i(py) = xa_i + (py - ya_i) dx_i / dy_i.
+// The float evaluation of e_i can disagree with the real sign only within 2.1 u |px - xa_i| of c_i
+// (u = 2^-24) and c_i is computed to a few ulp of its terms, so each bound is widened by
+// 2e-6 (1 + |xa_i| + (2 + |ya_i|) |dx_i / dy_i|): about 1e-4 of a pixel at R = 128 for ordinary edges,
+// never a missed pixel.  Slivers (|area| < 1e-5, where float edge signs need not be consistent with the
+// orientation) and near-horizontal edges add no constraint: the whole bbox row stays a candidate.
+// Phase C re-tests every candidate exactly, so the runs only need to be supersets.
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     int inc = v;
 #pragma unroll
@@ -574,48 +535,11 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         n_cands = 0;
         __syncwarp();
     };
-    // no item list and no per-pixel pre-test.  Phase A (lane / face) yields the clipped pixel bbox;
-    // the batch's bbox rows are then dealt out one per lane (owner found by a shuffle binary search over
-    // the prefix sums), each lane solves its row's pixel run in closed form (row_run) and appends the
-    // run's pixels to the warp's candidate list; phase C evaluates candidates exactly, 32 at a time.
-    auto sweep_rows = [&](unsigned int own, int n) {
-        int total;
-        const int excl = warp_excl_scan(n, lane, &total);
-        const int incl = excl + n;
-        for (int it0 = 0; it0 < total; it0 += 32) {
-            const int t = it0 + lane;
-            // owner = number of lanes whose inclusive prefix is <= t
-            int ow = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, incl, ow + step - 1);
-                if (v <= t) ow += step;
-            }
-            const bool live = t < total;
-            ow = live ? ow : 0;
-            const unsigned int o_pk = __shfl_sync(0xffffffffu, own, ow);
-            const int o_ex = __shfl_sync(0xffffffffu, excl, ow);
-            int ka = 0, kb = -1, j = 0;
-            const unsigned int fi = o_pk & 2047u;
-            if (live) {
-                j = ty0 + (int)(o_pk >> 25) + (t - o_ex);
-                row_run(s, vw, fi, j, tx0 + (int)((o_pk >> 11) & 127u), tx0 + (int)((o_pk >> 18) & 127u), &ka, &kb);
-            }
-            const int len = max(0, kb - ka + 1);
-            int c_total;
-            int slot = warp_excl_scan(len, lane, &c_total);
-            if (n_cands + c_total > RT_WCANDS) flush_cands();
-            if (c_total > RT_WCANDS) {                           // very large faces: evaluate in place
-                for (int k = ka; k <= kb; ++k) eval_and_commit(s, fi, k, j, tx0, ty0);
-                __syncwarp();
-                continue;
-            }
-            slot += n_cands;
-            const unsigned int base = fi | ((unsigned int)(j - ty0) << 11);
-            for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
-            n_cands += c_total;
-        }
-    };
+    // Phase A (lane / face): cull, exact clipped pixel bbox, and the three edge lines of the face in the
+    // form crossing(py) = m * py + c with the conservative margin of row_run() folded into c.
+    // Phase B (lane / bbox row): rows are dealt out by a shuffle binary search over the prefix sums of the
+    // row counts; the row's lane fetches the owner's lines by shuffle, intersects the three half-lines
+    // and appends the pixel run to the warp's candidate list.  Phase C: exact evaluation (flush_cands).
     while (tile_live) {
         int fb = 0;
         if (lane == 0) fb = atomicAdd(&s.counters[0], 32);
@@ -623,6 +547,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         if (fb >= F) break;
         const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
         int ia = 0, ib = -1, ja = 0, jb = -1;
+        float e_m[3] = {0.f, 0.f, 0.f}, e_c[3] = {0.f, 0.f, 0.f};
+        unsigned int e_flags = 0;          // bit i: edge i usable; bit 4 + i: edge i bounds the run from below (in x)
         if (f < F) {
             const unsigned int pk = s.fp[f];
             const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
@@ -640,12 +566,88 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                     ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
                     ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
                 }
+                if (ia <= ib && ja <= jb && fabsf(farea) >= 1e-5f) {     // slivers keep the whole bbox row
+                    // edge i of the oracle: e_i(px) = (px - xa) * dy - (py - ya) * dx, crossing at
+                    // px = xa + (py - ya) * dx / dy = m * py + (xa - ya * m).  The margin covers the oracle's
+                    // rounding (2.1 u |px - xa|), the approximate division and the cancellation in m * py + c.
+                    const float sg = farea > 0.f ? 1.f : -1.f;
+                    const float xa[3] = {x1, x2, x0}, ya[3] = {y1, y2, y0}, xb[3] = {x2, x0, x1}, yb[3] = {y2, y0, y1};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float dy = __fsub_rn(yb[i], ya[i]);
+                        const float m = __fdividef(__fsub_rn(xb[i], xa[i]), dy);
+                        const float am = fabsf(m);
+                        if (am < 1e30f) {                                  // else near-horizontal: no constraint
+                            const float dl = 2e-6f * (1.f + fabsf(xa[i]) + (2.f + fabsf(ya[i])) * am);
+                            const bool low = sg * dy > 0.f;
+                            e_m[i] = m;
+                            e_c[i] = fmaf(-ya[i], m, xa[i]) + (low ? -dl : dl);
+                            e_flags |= (1u << i) | (low ? 16u << i : 0u);
+                        }
+                    }
+                }
             }
         }
         const int n = (ib >= ia && jb >= ja) ? jb - ja + 1 : 0;
         const unsigned int own = (unsigned int)f | ((unsigned int)(ia - tx0) << 11) | ((unsigned int)(ib - tx0) << 18) |
                                  ((unsigned int)(ja - ty0) << 25);
-        sweep_rows(own, n);
+        int total;
+        const int excl = warp_excl_scan(n, lane, &total);
+        const int incl = excl + n;
+        for (int it0 = 0; it0 < total; it0 += 32) {
+            const int t = it0 + lane;
+            // owner = number of lanes whose inclusive prefix is <= t
+            int ow = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, ow + step - 1);
+                if (v <= t) ow += step;
+            }
+            const bool live = t < total;
+            ow = live ? ow : 0;
+            const unsigned int o_pk = __shfl_sync(0xffffffffu, own, ow);
+            const int o_ex = __shfl_sync(0xffffffffu, excl, ow);
+            const unsigned int o_fl = __shfl_sync(0xffffffffu, e_flags, ow);
+            float lo = -INFINITY, hi = INFINITY;
+            const int j = ty0 + (int)(o_pk >> 25) + (t - o_ex);
+            const float py = s.ys[live ? j : ty0];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float m = __shfl_sync(0xffffffffu, e_m[i], ow), c = __shfl_sync(0xffffffffu, e_c[i], ow);
+                const float v = fmaf(m, py, c);
+                if (o_fl & (1u << i)) {
+                    if (o_fl & (16u << i)) lo = fmaxf(lo, v);
+                    else hi = fminf(hi, v);
+                }
+            }
+            int ka = 0, kb = -1;
+            if (live) {
+                const int ia_o = tx0 + (int)((o_pk >> 11) & 127u), ib_o = tx0 + (int)((o_pk >> 18) & 127u);
+                if (vw.affine) {
+                    // direct mode: index = ax * x + bx exactly and xs is non-increasing, so x <= hi <=> index >=
+                    // ax * hi + bx; a thousandth of a pixel of slack covers the rounding of the map
+                    ka = max(ia_o, (int)ceilf(fmaf(vw.ax, hi, vw.bx) - 1e-3f));
+                    kb = min(ib_o, (int)floorf(fmaf(vw.ax, lo, vw.bx) + 1e-3f));
+                } else {
+                    ka = hi < INFINITY ? max(ia_o, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, hi)) : ia_o;
+                    kb = lo > -INFINITY ? min(ib_o, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, lo)) : ib_o;
+                }
+            }
+            const unsigned int fi = o_pk & 2047u;
+            const int len = max(0, kb - ka + 1);
+            int c_total;
+            int slot = warp_excl_scan(len, lane, &c_total);
+            if (n_cands + c_total > RT_WCANDS) flush_cands();
+            if (c_total > RT_WCANDS) {                           // very large faces: evaluate in place
+                for (int k = ka; k <= kb; ++k) eval_and_commit(s, fi, k, j, tx0, ty0);
+                __syncwarp();
+                continue;
+            }
+            slot += n_cands;
+            const unsigned int base = fi | ((unsigned int)(j - ty0) << 11);
+            for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
+            n_cands += c_total;
+        }
     }
     flush_cands();                                            // ---------------- phase C (remainder)
     __syncthreads();
