@@ -5,7 +5,7 @@
 // (:1113-1118) and pointsImgTo3D (:336-343).
 //
 // One CTA per hand, no host round trip: count the foreground pixels, choose `sample_num mod n`
-// of them without replacement by taking the smallest counter-based hash keys (3-pass radix select
+// of them without replacement by taking the smallest counter-based hash keys (2-pass radix select
 // in shared memory), and write [the whole foreground list repeated floor(sample_num / n) times |
 // the chosen ones], both in pixel order, exactly the layout :1141-1153 produces.  The sampled
 // subset is uniform and reproducible from `seed`; it is not torch.multinomial's stream (the
@@ -69,12 +69,15 @@ __device__ __forceinline__ int nearest_src(int dst, int n_in, float scale) {
     return s < n_in - 1 ? s : n_in - 1;
 }
 
+// 24-bit draw key of (seed, hand, pixel): a 32-bit avalanche mixer; ties (about one per four hands at
+// 3000 foreground pixels) are broken by pixel order
+#define PCL_NOKEY 0xffffffffu
 __device__ __forceinline__ unsigned pcl_key(unsigned long long seed, unsigned hand, unsigned pix) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)hand << 32) | pix);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (unsigned)(z >> 32);
+    unsigned x = pix + hand * 0x9E3779B9u + (unsigned)seed + (unsigned)(seed >> 32) * 0x85EBCA6Bu;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x >> 8;
 }
 
 __device__ __forceinline__ int block_sum(int v, int* s_red) {
@@ -84,18 +87,23 @@ __device__ __forceinline__ int block_sum(int v, int* s_red) {
     __syncthreads();
     int t = 0;
     for (int w = 0; w < PCL_WARPS; ++w) t += s_red[w];
+    __syncthreads();                               // the scratch may be rewritten right after the call
     return t;
 }
 
+// CACHE: the keys of all cells fit in shared memory (feature_size <= 128), so the image is read once
+// for the mask and once more for the kept cells; otherwise mask and key are recomputed in every pass.
+template <bool CACHE>
 __global__ void __launch_bounds__(PCL_THREADS)
 img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __restrict__ center,
                const float* __restrict__ cube, const float* __restrict__ M, float4 intr, float img_size, float flip,
                int sample_num, unsigned long long seed, int out_rows, float* __restrict__ pcl, int* __restrict__ count) {
+    extern __shared__ __align__(16) unsigned int s_keys[];
     __shared__ PclView view;
     __shared__ int s_hist[PCL_BINS];
     __shared__ int s_red[PCL_WARPS];
     __shared__ int s_scan[3][PCL_WARPS];
-    __shared__ int s_sel[3];          // chosen bin, items below it, (unused)
+    __shared__ int s_sel[2];          // chosen bin, items below it
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = fs * fs;
     const float* im = img + (size_t)b * R_in * R_in;
@@ -108,10 +116,30 @@ img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __r
         const int row = k / fs, col = k - row * fs;
         return R_in == fs ? im[k] : im[(size_t)nearest_src(row, R_in, scale) * R_in + nearest_src(col, R_in, scale)];
     };
+    // key of cell k, PCL_NOKEY for background
+    auto key_of = [&](int k) -> unsigned int {
+        if (CACHE) return s_keys[k];
+        return value(k) <= 0.99f ? pcl_key(seed, b, k) : PCL_NOKEY;
+    };
 
+    // every warp owns one contiguous segment of the cell sequence, so that ranks in pixel order are a
+    // block-level prefix over 16 warp totals plus ballots inside the warp (no per-chunk block barrier)
+    const int seg = ((npix + PCL_WARPS - 1) / PCL_WARPS + 31) & ~31;
+    const int k_lo = warp * seg, k_hi = min(npix, k_lo + seg);
     int mine = 0;
-    for (int k = tid; k < npix; k += PCL_THREADS) mine += value(k) <= 0.99f;
-    const int n = block_sum(mine, s_red);          // also publishes `view`
+    for (int k4 = k_lo + lane; k4 < k_hi; k4 += 128) {       // four independent loads in flight per lane
+        float val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) val[u] = k4 + 32 * u < k_hi ? value(k4 + 32 * u) : 1.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k4 + 32 * u;
+            const bool v = val[u] <= 0.99f;
+            if (CACHE && k < k_hi) s_keys[k] = v ? pcl_key(seed, b, k) : PCL_NOKEY;
+            mine += v;
+        }
+    }
+    const int n = block_sum(mine, s_red);          // also publishes `view` and the key cache
     if (tid == 0 && count) count[b] = n;
     float* out = pcl + (size_t)b * out_rows * 3;
     if (n == 0) {                                  // :1144 - an empty crop gives zeros
@@ -121,28 +149,23 @@ img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __r
     const int mult = sample_num > 0 ? sample_num / n : 1;
     const int k_rem = sample_num > 0 ? sample_num - mult * n : 0;
 
-    // k_rem-th smallest key among the foreground pixels: radix select over 12 + 12 + 8 bits
+    // k_rem-th smallest key among the foreground cells: radix select over 12 + 12 bits
     unsigned prefix = 0, prefix_mask = 0;
     int need = k_rem;                              // rank (1-based) still to be located
     if (k_rem > 0) {
-        const int shifts[3] = {20, 8, 0}, widths[3] = {12, 12, 8};
-        for (int pass = 0; pass < 3; ++pass) {
-            const int nb = 1 << widths[pass];
-            for (int i = tid; i < nb; i += PCL_THREADS) s_hist[i] = 0;
+        const int per = PCL_BINS / PCL_THREADS;    // consecutive bins per thread
+        for (int pass = 0; pass < 2; ++pass) {
+            const int shift = pass == 0 ? 12 : 0;
+            for (int i = tid; i < PCL_BINS; i += PCL_THREADS) s_hist[i] = 0;
             __syncthreads();
             for (int k = tid; k < npix; k += PCL_THREADS) {
-                if (value(k) <= 0.99f) {
-                    const unsigned key = pcl_key(seed, b, k);
-                    if ((key & prefix_mask) == prefix) atomicAdd(&s_hist[(key >> shifts[pass]) & (nb - 1)], 1);
-                }
+                const unsigned key = key_of(k);
+                if (key != PCL_NOKEY && (key & prefix_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & (PCL_BINS - 1)], 1);
             }
             __syncthreads();
-            // each thread owns nb / 512 consecutive bins (at least one thread-bin for the 256-bin pass)
-            const int per = nb >= PCL_THREADS ? nb / PCL_THREADS : 1;
             const int b0 = tid * per;
             int local = 0;
-            if (b0 < nb)
-                for (int i = 0; i < per; ++i) local += s_hist[b0 + i];
+            for (int i = 0; i < per; ++i) local += s_hist[b0 + i];
             int incl = local;
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -152,7 +175,7 @@ img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __r
             __syncthreads();
             int before = incl - local;
             for (int w = 0; w < warp; ++w) before += s_scan[0][w];
-            if (b0 < nb && before < need && need <= before + local) {
+            if (before < need && need <= before + local) {
                 int cum = before;
                 for (int i = 0; i < per; ++i) {
                     const int h = s_hist[b0 + i];
@@ -161,60 +184,72 @@ img2pcl_kernel(int R_in, int fs, const float* __restrict__ img, const float* __r
                 }
             }
             __syncthreads();
-            prefix |= (unsigned)s_sel[0] << shifts[pass];
-            prefix_mask |= (unsigned)(nb - 1) << shifts[pass];
+            prefix |= (unsigned)s_sel[0] << shift;
+            prefix_mask |= (unsigned)(PCL_BINS - 1) << shift;
             need -= s_sel[1];
             __syncthreads();
         }
     }
     const unsigned thr = prefix;                   // keys < thr are all taken, `need` of the keys == thr
 
-    // ordered compaction
+    // ordered compaction: per-warp totals of (foreground, key < thr, key == thr) -> exclusive prefix over
+    // the warps -> each warp walks its segment with ballots only
+    int wv = 0, wl = 0, we = 0;
+    for (int k = k_lo + lane; k < k_hi; k += 32) {
+        const unsigned key = key_of(k);
+        wv += key != PCL_NOKEY;
+        wl += key != PCL_NOKEY && k_rem > 0 && key < thr;
+        we += key != PCL_NOKEY && k_rem > 0 && key == thr;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        wv += __shfl_xor_sync(0xffffffffu, wv, o);
+        wl += __shfl_xor_sync(0xffffffffu, wl, o);
+        we += __shfl_xor_sync(0xffffffffu, we, o);
+    }
+    if (lane == 0) { s_scan[0][warp] = wv; s_scan[1][warp] = wl; s_scan[2][warp] = we; }
+    __syncthreads();
     int base_valid = 0, base_less = 0, base_eq = 0;
-    for (int k0 = 0; k0 < npix; k0 += PCL_THREADS) {
-        const int k = k0 + tid;
-        float val = 1.f;
-        bool v = false, less = false, eq = false;
-        if (k < npix) {
-            val = value(k);
-            v = val <= 0.99f;
-            if (v && k_rem > 0) {
-                const unsigned key = pcl_key(seed, b, k);
-                less = key < thr;
-                eq = key == thr;
-            }
+    for (int w = 0; w < warp; ++w) { base_valid += s_scan[0][w]; base_less += s_scan[1][w]; base_eq += s_scan[2][w]; }
+    const unsigned lower = (1u << lane) - 1u;
+    for (int k4 = k_lo; k4 < k_hi; k4 += 128) {
+        // keys and depths of four 32-cell chunks are fetched up front, then consumed in pixel order
+        unsigned int key4[4];
+        float val4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k4 + 32 * u + lane;
+            key4[u] = k < k_hi ? key_of(k) : PCL_NOKEY;
+            val4[u] = k < k_hi ? value(k) : 1.f;
         }
-        const unsigned mv = __ballot_sync(0xffffffffu, v), ml = __ballot_sync(0xffffffffu, less),
-                       me = __ballot_sync(0xffffffffu, eq);
-        const unsigned lower = (1u << lane) - 1u;
-        __syncthreads();
-        if (lane == 0) { s_scan[0][warp] = __popc(mv); s_scan[1][warp] = __popc(ml); s_scan[2][warp] = __popc(me); }
-        __syncthreads();
-        int rv = base_valid + __popc(mv & lower), rl = base_less + __popc(ml & lower), re = base_eq + __popc(me & lower);
-        int tv = 0, tl = 0, te = 0;
-        for (int w = 0; w < PCL_WARPS; ++w) {
-            const int a = s_scan[0][w], c = s_scan[1][w], e = s_scan[2][w];
-            if (w < warp) { rv += a; rl += c; re += e; }
-            tv += a; tl += c; te += e;
-        }
-        if (v) {
-            const int row = k / fs, col = k - row * fs;
-            float xyz[3], q[3];
-            pcl_point(view, row, col, fs, val, xyz);
-            pcl_normalise(view, xyz, q);
-            for (int m = 0; m < mult; ++m) {
-                float* o = out + ((size_t)m * n + rv) * 3;
-                o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k4 + 32 * u + lane;
+            const unsigned key = key4[u];
+            const bool v = key != PCL_NOKEY;
+            const bool less = v && k_rem > 0 && key < thr, eq = v && k_rem > 0 && key == thr;
+            const unsigned mv = __ballot_sync(0xffffffffu, v), ml = __ballot_sync(0xffffffffu, less),
+                           me = __ballot_sync(0xffffffffu, eq);
+            if (v) {
+                const int rv = base_valid + __popc(mv & lower), rl = base_less + __popc(ml & lower),
+                          re = base_eq + __popc(me & lower);
+                const int row = k / fs, col = k - row * fs;
+                float xyz[3], q[3];
+                pcl_point(view, row, col, fs, val4[u], xyz);
+                pcl_normalise(view, xyz, q);
+                for (int m = 0; m < mult; ++m) {
+                    float* o = out + ((size_t)m * n + rv) * 3;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+                }
+                // selected rank in pixel order: all `less` so far plus the admitted ties so far
+                const bool take = less || (eq && re < need);
+                if (take) {
+                    const int r = rl + (re < need ? re : need);
+                    float* o = out + ((size_t)mult * n + r) * 3;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+                }
             }
-            // selected rank in pixel order: all `less` so far plus the admitted ties so far
-            const bool take = less || (eq && re < need);
-            if (take) {
-                const int r = rl + (re < need ? re : need);
-                float* o = out + ((size_t)mult * n + r) * 3;
-                o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
-            }
+            base_valid += __popc(mv); base_less += __popc(ml); base_eq += __popc(me);
         }
-        base_valid += tv; base_less += tl; base_eq += te;
     }
 }
 
@@ -226,9 +261,20 @@ extern "C" int dsf_img2pcl(int batch, int R_in, int feature_size, const float* i
     DSF_REQUIRE(R_in >= 2 && feature_size >= 2 && feature_size <= 1024, "feature_size must be in [2,1024]");
     DSF_REQUIRE(sample_num >= 0, "sample_num must be >= 0");
     const int out_rows = sample_num > 0 ? sample_num : feature_size * feature_size;
-    img2pcl_kernel<<<batch, PCL_THREADS, 0, (cudaStream_t)stream>>>(
-        R_in, feature_size, img, center3d, cube, M, make_float4(intr4[0], intr4[1], intr4[2], intr4[3]), img_size, flip,
-        sample_num, seed, out_rows, pcl, count);
+    const float4 in4 = make_float4(intr4[0], intr4[1], intr4[2], intr4[3]);
+    if (feature_size <= 128) {
+        const size_t smem = (size_t)feature_size * feature_size * sizeof(unsigned int);
+        static bool attr_set = false;
+        if (!attr_set) {
+            DSF_CHECK_CUDA(cudaFuncSetAttribute(img2pcl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+            attr_set = true;
+        }
+        img2pcl_kernel<true><<<batch, PCL_THREADS, smem, (cudaStream_t)stream>>>(
+            R_in, feature_size, img, center3d, cube, M, in4, img_size, flip, sample_num, seed, out_rows, pcl, count);
+    } else {
+        img2pcl_kernel<false><<<batch, PCL_THREADS, 0, (cudaStream_t)stream>>>(
+            R_in, feature_size, img, center3d, cube, M, in4, img_size, flip, sample_num, seed, out_rows, pcl, count);
+    }
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
