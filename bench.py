@@ -415,6 +415,41 @@ def run_ours(args):
                                      "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
                                      "note": "brute-force ICPLoss fwd+bwd; FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
+        # config C3 (BASELINE.json configs[3]): 256x256, 3 camera views per hand, batch 512, depth + silhouette
+        # (union-mask) loss through the modular autograd API: MANO once per hand, per view a rigid rotation
+        # about center3d (RotationPoints), rasterise, m2d loss, backward to the 62 parameters
+        from dsf_b200.mano_layer import Render, RotationPoints
+        from dsf_b200.render_loss import m2d_loss
+        b3, V3, R3 = 512, 3, 256
+        rnd3 = Render(make_synthetic_mano(0), "nyu", (588.03, 587.07, 320.0, 240.0), (640, 480), (R3, R3), mode="direct")
+        i3 = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(b3, seed=9).items()}
+        rot3 = torch.tensor([[0.0, 0.0, 0.0], [0.0, 2 * np.pi / 3, 0.0], [0.0, -2 * np.pi / 3, 0.0]], device=dev).repeat(b3, 1)
+        c3v, cube3v = i3["center3d"].repeat_interleave(V3, 0), i3["cube"].repeat_interleave(V3, 0)
+
+        def c3_images(params):
+            v, j = rnd3.mano_layer.get_mano_vertices(params[:, :3], params[:, 3:48], params[:, 48:58], params[:, 58:],
+                                                     global_scale=1 / 125)
+            vw = (v * i3["cube"][:, None] / 2 + i3["center3d"][:, None]).repeat_interleave(V3, 0)
+            jw = (j * i3["cube"][:, None] / 2 + i3["center3d"][:, None]).repeat_interleave(V3, 0)
+            vr, _ = RotationPoints(vw, jw, c3v, rot3)
+            return rnd3._rasterize(vr, c3v, cube3v)[0]
+
+        with torch.no_grad():
+            tgt3 = c3_images(i3["params_target"]).clone()
+        pg3 = i3["params"].clone().requires_grad_(True)
+
+        def c3_step():
+            m2d_loss(tgt3, c3_images(pg3)).backward()
+            pg3.grad = None
+
+        c3_step()
+        t_c3 = time_region(c3_step, 10)
+        c3_bytes = 6 * R3 * R3 * 4 + 10100 + 180
+        other["C3_multiview_256_batch512"] = {
+            "hands": b3, "views": V3, "crop": R3, "ms_fwd_bwd": t_c3, "fits_per_s": b3 / (t_c3 * 1e-3),
+            "step_hbm_frac": c3_bytes * b3 / (t_c3 * 1e-3) / 1e9 / peak,
+            "note": "modular autograd path (image returned, loss as a separate kernel, torch ops for the view rotation)"}
+        del tgt3, rnd3
         # "next" rows: depth crop -> 2048-point cloud (Img2pcl) and the intersection-volume metric (I1)
         from dsf_b200.intersection import PartTopology, intersect_counts
         from dsf_b200.pcl import Img2pcl

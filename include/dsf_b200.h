@@ -99,7 +99,9 @@ int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParams* p, float
  * mode 1 "literal": the S x S raster -> (H,W) resize -> crop chain, evaluated only at the
  *         raster pixel each crop pixel reads (S = max(W,H)); M_in (B,3,3) optional (M_render /
  *         getDepth pass their own, must be axis-aligned), else recomputed like render() does.
- * Outputs: view (B,16) = [fxn,fyn,pxn,pyn, zc,zhalf,bg, ax,bx,ay,by, x_lo,x_hi,y_lo,y_hi(as float), 0],
+ * Outputs: view (B,16) = [fxn,fyn,pxn,pyn, zc,zhalf,bg, ax,bx,ay,by, x_lo,x_hi,y_lo,y_hi(as float), affine]
+ *          (affine = 1 when sample index = a * ndc + b holds exactly, i.e. mode 0; the rasteriser then
+ *          converts run ends analytically instead of searching xs),
  *          xs (B,R), ys (B,R) NDC sample coordinates (NaN = reads zero padding), M_out (B,3,3) or NULL. */
 int dsf_view_setup(int mode, int batch, const float* center3d, const float* cube,
                    const float* intr4, int W, int H, int R, const float* M_in, float* view,
