@@ -79,6 +79,8 @@ SIGNATURES = {
     "dsf_target_from_u16": (_I, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP]),
     "dsf_intersect_workspace_bytes": (C.c_long, [_I, _I, _I, _I]),
     "dsf_intersect_vox": (_I, [_I, _I, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_rotate_points": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_rotate_points_backward": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_uvd_img_to_xyz": (_I, [_I, _I, _VP, _VP, _VP, _VP, c_float_p, _F, _F, _VP, _VP, _VP]),
 }
 

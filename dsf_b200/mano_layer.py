@@ -370,12 +370,50 @@ def batch_rodrigues(theta):
     return quat2mat(torch.cat([torch.cos(half), torch.sin(half) * axis], dim=1))
 
 
+class _RotatePoints(torch.autograd.Function):
+    """out = R (p - c) + c in one kernel (dsf_rotate_points); the cotangents of the points, of R and of
+    c come from one more (dsf_rotate_points_backward) - instead of B*N 3x3 GEMVs in torch.matmul."""
+
+    @staticmethod
+    def forward(ctx, pts, Rm, center):
+        lib = L.lib()
+        pts_c, Rm_c = L.f32c(pts), L.f32c(Rm)
+        cen_c = None if center is None else L.f32c(center)
+        B, n = pts_c.shape[0], pts_c.shape[1]
+        out = torch.empty_like(pts_c)
+        L.check(lib.dsf_rotate_points(B, n, pts_c.data_ptr(), Rm_c.data_ptr(),
+                                      None if cen_c is None else cen_c.data_ptr(), out.data_ptr(), L.stream_ptr()))
+        ctx.save_for_backward(pts_c, Rm_c, cen_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        pts_c, Rm_c, cen_c = ctx.saved_tensors
+        g = L.f32c(g)
+        B, n = pts_c.shape[0], pts_c.shape[1]
+        need_p, need_R, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and cen_c is not None
+        g_p = torch.empty_like(pts_c) if need_p else None
+        g_R = torch.empty_like(Rm_c) if need_R else None
+        g_c = torch.empty_like(cen_c) if need_c else None
+        if need_p or need_R or need_c:
+            ptr = lambda t: None if t is None else t.data_ptr()
+            L.check(lib.dsf_rotate_points_backward(B, n, pts_c.data_ptr(), Rm_c.data_ptr(), ptr(cen_c), g.data_ptr(),
+                                                   ptr(g_p), ptr(g_R), ptr(g_c), L.stream_ptr()))
+        return g_p, g_R, g_c
+
+
 def RotationPoints(verts, joints, center3d, rot):
-    rot_mat = (batch_rodrigues(rot) if rot.size(-1) == 3 else quat2mat(rot)).unsqueeze(1)
-    c = center3d.unsqueeze(1)
-    rv = torch.matmul(rot_mat, (verts - c).unsqueeze(-1)).squeeze(-1)
-    rj = torch.matmul(rot_mat, (joints - c).unsqueeze(-1)).squeeze(-1)
-    return rv + c, rj + c
+    """mano_layer.py:874-885: rotate verts (B,N,3) and joints (B,J,3) about center3d (B,3) by rot
+    (axis-angle (B,3) or quaternion (B,4))."""
+    rot_mat = batch_rodrigues(rot) if rot.size(-1) == 3 else quat2mat(rot)
+    return _RotatePoints.apply(verts, rot_mat, center3d), _RotatePoints.apply(joints, rot_mat, center3d)
+
+
+def RotationNormalPoints(points, rot):
+    """mano_layer.py:888-895: pure rotation of (B,N,3) points."""
+    rot_mat = batch_rodrigues(rot) if rot.size(-1) == 3 else quat2mat(rot)
+    return _RotatePoints.apply(points, rot_mat, None)
 
 
 # ------------------------------------------------------------------------------------------------

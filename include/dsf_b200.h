@@ -257,6 +257,16 @@ int dsf_intersect_vox(int batch, int n_verts, const float* verts, int n_caps, co
                       long long* voxel_counts, double* volume, int* status, void* workspace,
                       dsfStream_t stream);
 
+/* R5 helper - replaces RotationPoints / RotationNormalPoints (render_model/mano_layer.py:874-895), the
+ * rigid rotation that makes the extra camera views: out = R (p - c) + c with R (B,3,3) row-major,
+ * pts / out (B,n,3), center3d (B,3) or NULL (pure rotation).  Backward: g_pts = R^T g and, when the
+ * pointers are given, g_R (B,3,3) = sum_n g_n (p_n - c)^T and g_center (B,3) = sum_n (g_n - R^T g_n). */
+int dsf_rotate_points(int batch, int n, const float* pts, const float* Rm, const float* center3d,
+                      float* out, dsfStream_t stream);
+int dsf_rotate_points_backward(int batch, int n, const float* pts, const float* Rm, const float* center3d,
+                               const float* g_out, float* g_pts, float* g_R, float* g_center,
+                               dsfStream_t stream);
+
 /* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
 int dsf_last_launch_count(void);
 
