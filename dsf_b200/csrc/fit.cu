@@ -87,3 +87,158 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     rc = dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Render.render as two calls (forward, backward) for the autograd drop-in: the reference's
+// Render.render (mano_layer.py:1071-1097) returns (img, joint_uvd, joint_xyz, mesh_xyz); left as
+// separate torch ops around the kernels it costs ~110 launches and 1.6 ms of host time per step at
+// any batch size, here it is 5 + 4 launches.
+// ------------------------------------------------------------------------------------------------
+#define AUX_THREADS 128
+
+// joints / verts normalised (get_mano_vertices with global_scale 1/125) -> the three auxiliary outputs,
+// same operation order as the reference: hand = x * cube / 2 + center (:1078-1079), JointTrans (:1301-1309)
+// with points3DToImg (:1318-1324), joint_xyz / mesh_xyz = (hand - center) / cube * 2 (:1093-1094)
+__global__ void __launch_bounds__(AUX_THREADS)
+render_aux_kernel(const float* __restrict__ verts, const float* __restrict__ joints, const float* __restrict__ center,
+                  const float* __restrict__ cube, const float* __restrict__ M, float fx, float fy, float px, float py,
+                  float crop, float* __restrict__ joint_uvd, float* __restrict__ joint_xyz, float* __restrict__ mesh_xyz) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float c[3] = {center[3 * b], center[3 * b + 1], center[3 * b + 2]};
+    const float q[3] = {cube[3 * b], cube[3 * b + 1], cube[3 * b + 2]};
+    if (mesh_xyz)
+        for (int i = tid; i < NVW * 3; i += AUX_THREADS) {
+            const int k = i % 3;
+            const float hv = __fadd_rn(__fdiv_rn(__fmul_rn(verts[(size_t)b * NVW * 3 + i], q[k]), 2.f), c[k]);
+            mesh_xyz[(size_t)b * NVW * 3 + i] = __fmul_rn(__fdiv_rn(__fsub_rn(hv, c[k]), q[k]), 2.f);
+        }
+    if (tid < NJOUT) {
+        const float* j = joints + ((size_t)b * NJOUT + tid) * 3;
+        float h[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) h[k] = __fadd_rn(__fdiv_rn(__fmul_rn(j[k], q[k]), 2.f), c[k]);
+        if (joint_xyz)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                joint_xyz[((size_t)b * NJOUT + tid) * 3 + k] = __fmul_rn(__fdiv_rn(__fsub_rn(h[k], c[k]), q[k]), 2.f);
+        if (joint_uvd) {
+            const float* m = M + 9 * (size_t)b;
+            const float u = __fadd_rn(__fdiv_rn(__fmul_rn(h[0], fx), __fadd_rn(h[2], 1e-8f)), px);
+            const float v = __fadd_rn(__fdiv_rn(__fmul_rn(h[1], fy), h[2]), py);
+            const float ut = __fadd_rn(__fadd_rn(__fmul_rn(m[0], u), __fmul_rn(m[1], v)), m[2]);
+            const float vt = __fadd_rn(__fadd_rn(__fmul_rn(m[3], u), __fmul_rn(m[4], v)), m[5]);
+            float* o = joint_uvd + ((size_t)b * NJOUT + tid) * 3;
+            o[0] = __fsub_rn(__fmul_rn(__fdiv_rn(ut, crop), 2.f), 1.f);
+            o[1] = __fsub_rn(__fmul_rn(__fdiv_rn(vt, crop), 2.f), 1.f);
+            o[2] = __fdiv_rn(__fsub_rn(h[2], c[2]), __fdiv_rn(q[2], 2.f));
+        }
+    }
+}
+
+// cotangents of the auxiliary outputs -> g_verts += g_mesh_xyz, g_joints = chain of g_joint_uvd + g_joint_xyz
+__global__ void __launch_bounds__(AUX_THREADS)
+render_aux_bwd_kernel(const float* __restrict__ joints, const float* __restrict__ center, const float* __restrict__ cube,
+                      const float* __restrict__ M, float fx, float fy, float crop, const float* __restrict__ g_uvd,
+                      const float* __restrict__ g_jxyz, const float* __restrict__ g_mxyz, int have_raster,
+                      float* __restrict__ g_verts, float* __restrict__ g_joints) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < NVW * 3; i += AUX_THREADS) {
+        const size_t o = (size_t)b * NVW * 3 + i;
+        const float a = have_raster ? g_verts[o] : 0.f;
+        g_verts[o] = g_mxyz ? a + g_mxyz[o] : a;          // d mesh_xyz / d verts = 1
+    }
+    if (tid < NJOUT) {
+        const size_t o = ((size_t)b * NJOUT + tid) * 3;
+        float g[3] = {0.f, 0.f, 0.f};
+        if (g_jxyz) { g[0] = g_jxyz[o]; g[1] = g_jxyz[o + 1]; g[2] = g_jxyz[o + 2]; }
+        if (g_uvd) {
+            const float q[3] = {cube[3 * b], cube[3 * b + 1], cube[3 * b + 2]};
+            const float* j = joints + o;
+            const float hx = j[0] * q[0] * 0.5f + center[3 * b], hy = j[1] * q[1] * 0.5f + center[3 * b + 1],
+                        hz = j[2] * q[2] * 0.5f + center[3 * b + 2];
+            const float* m = M + 9 * (size_t)b;
+            const float s = 2.f / crop;
+            const float gu = (g_uvd[o] * m[0] + g_uvd[o + 1] * m[3]) * s, gv = (g_uvd[o] * m[1] + g_uvd[o + 1] * m[4]) * s;
+            const float ize = 1.f / (hz + 1e-8f), iz = 1.f / hz;
+            const float ghx = gu * fx * ize, ghy = gv * fy * iz;
+            const float ghz = -gu * hx * fx * ize * ize - gv * hy * fy * iz * iz + g_uvd[o + 2] / (q[2] * 0.5f);
+            g[0] += ghx * q[0] * 0.5f; g[1] += ghy * q[1] * 0.5f; g[2] += ghz * q[2] * 0.5f;
+        }
+        g_joints[o] = g[0]; g_joints[o + 1] = g[1]; g_joints[o + 2] = g[2];
+    }
+}
+
+static void render_params(const float* params, int ld, int quat_dim, float* g_params, DsfManoParams* p, DsfManoGrads* g) {
+    p->quat = params; p->ld_quat = ld; p->quat_dim = quat_dim;
+    p->theta = params + quat_dim; p->ld_theta = ld; p->ncomp = 45;
+    p->beta = params + quat_dim + 45; p->ld_beta = ld;
+    p->cam = params + quat_dim + 55; p->ld_cam = ld;
+    if (g) {
+        g->quat = g_params; g->ld_quat = ld;
+        g->theta = g_params + quat_dim; g->ld_theta = ld;
+        g->beta = g_params + quat_dim + 45; g->ld_beta = ld;
+        g->cam = g_params + quat_dim + 55; g->ld_cam = ld;
+    }
+}
+
+extern "C" long dsf_render_workspace_floats(int batch) {
+    return (long)batch * (WS_PER_HAND + NVW * 3 + NJOUT * 3);
+}
+
+extern "C" int dsf_render_forward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
+                                  const float* center3d, const float* cube, const float* view, const float* xs,
+                                  const float* ys, const float* M, const float* intr4, float* img, int* pix_to_face,
+                                  float* verts, float* joints, float* joint_uvd, float* joint_xyz, float* mesh_xyz,
+                                  float* workspace, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && M && intr4, "null input");
+    DSF_REQUIRE(img && pix_to_face && verts && joints && workspace, "null output");
+    DSF_REQUIRE(batch > 0 && batch <= 65535, "batch must be in [1,65535] per call");
+    DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
+    DSF_REQUIRE((quat_dim == 3 || quat_dim == 4) && ld_params >= quat_dim + 59, "params must be (B, 62 | 63)");
+    cudaStream_t st = (cudaStream_t)stream;
+    DsfManoParams p;
+    render_params(params, ld_params, quat_dim, nullptr, &p, nullptr);
+    int rc = dsf_mano_forward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, nullptr, workspace, st);
+    if (rc) return rc;
+    rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr, nullptr,
+                                 nullptr, nullptr, 0.99f, nullptr, nullptr, st);
+    if (rc) return rc;
+    if (joint_uvd || joint_xyz || mesh_xyz) {
+        render_aux_kernel<<<batch, AUX_THREADS, 0, st>>>(verts, joints, center3d, cube, M, intr4[0], intr4[1], intr4[2],
+                                                         intr4[3], (float)R, joint_uvd, joint_xyz, mesh_xyz);
+        DSF_CHECK_LAUNCH();
+    }
+    return DSF_OK;
+}
+
+extern "C" int dsf_render_backward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
+                                   const float* center3d, const float* cube, const float* view, const float* xs,
+                                   const float* ys, const float* M, const float* intr4, const float* verts,
+                                   const float* joints, const int* pix_to_face, const float* g_img,
+                                   const float* g_joint_uvd, const float* g_joint_xyz, const float* g_mesh_xyz,
+                                   float* g_params, float* workspace, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && M && intr4 && verts && joints && pix_to_face,
+                "null input");
+    DSF_REQUIRE(g_params && workspace, "null output");
+    DSF_REQUIRE(batch > 0 && batch <= 65535, "batch must be in [1,65535] per call");
+    DSF_REQUIRE((quat_dim == 3 || quat_dim == 4) && ld_params >= quat_dim + 59, "params must be (B, 62 | 63)");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* g_verts = workspace + (size_t)batch * WS_PER_HAND;
+    float* g_joints = g_verts + (size_t)batch * NVW * 3;
+    DsfManoParams p;
+    DsfManoGrads g;
+    render_params(params, ld_params, quat_dim, g_params, &p, &g);
+    int rc;
+    if (g_img) {
+        rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, g_img, g_verts,
+                                      nullptr, nullptr, nullptr, 0.f, 0.99f, nullptr, st);
+        if (rc) return rc;
+    }
+    render_aux_bwd_kernel<<<batch, AUX_THREADS, 0, st>>>(joints, center3d, cube, M, intr4[0], intr4[1], (float)R,
+                                                         g_joint_uvd, g_joint_xyz, g_mesh_xyz, g_img ? 1 : 0, g_verts,
+                                                         g_joints);
+    DSF_CHECK_LAUNCH();
+    return dsf_mano_backward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, g_verts, g_joints, &g, workspace, st);
+}

@@ -370,6 +370,54 @@ def batch_rodrigues(theta):
     return quat2mat(torch.cat([torch.cos(half), torch.sin(half) * axis], dim=1))
 
 
+class _RenderFunction(torch.autograd.Function):
+    """Render.render in one forward and one backward call (dsf_render_forward / dsf_render_backward):
+    MANO, placement, rasterisation + normalisation and the three auxiliary outputs, then their adjoints
+    back to the (B, 62 | 63) parameter block."""
+
+    @staticmethod
+    def forward(ctx, render, model_paras, center3d, cube_size, view, xs, ys, M):
+        lib = L.lib()
+        layer = render.mano_layer
+        prm = L.f32c(model_paras)
+        center3d, cube_size = L.f32c(center3d), L.f32c(cube_size)
+        B, ld = prm.shape
+        qd = 4 if ld == 63 else 3
+        R = xs.shape[1]
+        dev = prm.device
+        img = torch.empty(B, 1, R, R, device=dev)
+        p2f = torch.empty(B, R, R, dtype=torch.int32, device=dev)
+        verts = torch.empty(B, L.NVW, 3, device=dev)
+        joints = torch.empty(B, L.NJOUT, 3, device=dev)
+        juvd, jxyz, mxyz = torch.empty_like(joints), torch.empty_like(joints), torch.empty_like(verts)
+        ws = torch.empty(lib.dsf_render_workspace_floats(B), device=dev)
+        L.check(lib.dsf_render_forward(layer._handle, B, R, prm.data_ptr(), ld, qd, center3d.data_ptr(),
+                                       cube_size.data_ptr(), view.data_ptr(), xs.data_ptr(), ys.data_ptr(), M.data_ptr(),
+                                       render._intr, img.data_ptr(), p2f.data_ptr(), verts.data_ptr(), joints.data_ptr(),
+                                       juvd.data_ptr(), jxyz.data_ptr(), mxyz.data_ptr(), ws.data_ptr(), L.stream_ptr()))
+        ctx.render = render
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
+        ctx.save_for_backward(prm, center3d, cube_size, view, xs, ys, M, verts, joints, p2f, ws)
+        ctx.mark_non_differentiable(p2f)
+        return img, juvd, jxyz, mxyz, p2f
+
+    @staticmethod
+    def backward(ctx, g_img, g_juvd, g_jxyz, g_mxyz, _g_p2f):
+        lib = L.lib()
+        prm, center3d, cube_size, view, xs, ys, M, verts, joints, p2f, ws = ctx.saved_tensors
+        B, ld = prm.shape
+        qd = 4 if ld == 63 else 3
+        R = xs.shape[1]
+        gs = [None if g is None else L.f32c(g) for g in (g_img, g_juvd, g_jxyz, g_mxyz)]
+        g_prm = torch.empty_like(prm)
+        L.check(lib.dsf_render_backward(ctx.render.mano_layer._handle, B, R, prm.data_ptr(), ld, qd, center3d.data_ptr(),
+                                        cube_size.data_ptr(), view.data_ptr(), xs.data_ptr(), ys.data_ptr(), M.data_ptr(),
+                                        ctx.render._intr, verts.data_ptr(), joints.data_ptr(), p2f.data_ptr(),
+                                        L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), L.ptr(gs[3]), g_prm.data_ptr(),
+                                        ws.data_ptr(), L.stream_ptr()))
+        return None, g_prm, None, None, None, None, None, None
+
+
 class _RotatePoints(torch.autograd.Function):
     """out = R (p - c) + c in one kernel (dsf_rotate_points); the cotangents of the points, of R and of
     c come from one more (dsf_rotate_points_backward) - instead of B*N 3x3 GEMVs in torch.matmul."""
@@ -488,6 +536,19 @@ class Render(nn.Module):
 
     # -- R5 entry points -----------------------------------------------------------------------------
     def render(self, model_paras, center3d, cube_size, M=None):
+        """mano_layer.py:1071-1097 -> (img, joint_uvd, joint_xyz, mesh_xyz).  The whole chain is one
+        autograd node (two C-ABI calls); M is recomputed from center3d / cube_size like the reference
+        does (:1088-1089), the argument is accepted and ignored for signature compatibility.
+        Gradients flow to model_paras (center3d and cube_size are data)."""
+        if model_paras.size(-1) not in (62, 63):
+            raise ValueError("model_paras must be (B, 62) or (B, 63)")
+        view, xs, ys, M_used = self._view(center3d, cube_size)
+        img, joint_uvd, joint_xyz, mesh_xyz, _ = _RenderFunction.apply(self, model_paras, center3d, cube_size, view, xs,
+                                                                       ys, M_used)
+        return img, joint_uvd, joint_xyz, mesh_xyz
+
+    def render_modular(self, model_paras, center3d, cube_size, M=None):
+        """The same computation composed from the individual autograd ops (MANO, raster, torch helpers)."""
         quat, theta, beta, cam = self._split(model_paras)
         verts, joints = self.mano_layer.get_mano_vertices(quat, theta, beta, cam, global_scale=1 / 125)
         hand_verts = verts * cube_size.unsqueeze(1) / 2 + center3d.unsqueeze(1)

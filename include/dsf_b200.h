@@ -203,6 +203,27 @@ int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const 
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
                  float* workspace, dsfStream_t stream);
 
+/* R5 - Render.render (render_model/mano_layer.py:1071-1097) as one forward and one backward call for the
+ * autograd drop-in: params (B, ld_params >= 62 | 63) = [quat(3|4) | theta45 | beta10 | scale, trans3],
+ * view / xs / ys / M from dsf_view_setup.  Outputs: img (B,R,R) normalised depth, pix_to_face (B,R,R),
+ * verts (B,779,3) / joints (B,21,3) normalised (saved for backward), and the reference's other three
+ * return values joint_uvd (B,21,3) (JointTrans :1301-1309), joint_xyz (B,21,3), mesh_xyz (B,779,3)
+ * (:1093-1094; any of the three may be NULL).  workspace: dsf_render_workspace_floats(batch) floats, kept
+ * untouched between forward and backward.  Backward: cotangents (any may be NULL) -> g_params, same
+ * layout / leading dimension as params (only the 62 | 63 parameter columns are written). */
+long dsf_render_workspace_floats(int batch);
+int dsf_render_forward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
+                       const float* center3d, const float* cube, const float* view, const float* xs,
+                       const float* ys, const float* M, const float* intr4, float* img, int* pix_to_face,
+                       float* verts, float* joints, float* joint_uvd, float* joint_xyz, float* mesh_xyz,
+                       float* workspace, dsfStream_t stream);
+int dsf_render_backward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
+                        const float* center3d, const float* cube, const float* view, const float* xs,
+                        const float* ys, const float* M, const float* intr4, const float* verts,
+                        const float* joints, const int* pix_to_face, const float* g_img,
+                        const float* g_joint_uvd, const float* g_joint_xyz, const float* g_mesh_xyz,
+                        float* g_params, float* workspace, dsfStream_t stream);
+
 /* "next" row f1 - replaces loader.crop_hand (data/render_loader.py:1209-1227, with uvdImg2xyzImg
  * :1190-1200): pixels whose back-projected point falls outside the box around the teacher skeleton
  * (joints (B,nj,3) normalised; offsets in mm, reference defaults 25/20/20) become background 1.0.
