@@ -415,6 +415,29 @@ def run_ours(args):
                                      "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
                                      "note": "brute-force ICPLoss fwd+bwd; FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
+        # the reference's own call sequence through the drop-in classes: Render.render -> m2d loss -> backward
+        # (one autograd node + the loss op), literal 640^2 -> 480x640 -> 128^2 pixel chain, batch 128 (configs[1])
+        from dsf_b200.mano_layer import Render as _Render
+        from dsf_b200.render_loss import m2d_loss as _m2d
+        for bapi in (128, 1024):
+            rapi = _Render(make_synthetic_mano(0), "nyu", (588.03, 587.07, 320.0, 240.0), (640, 480), (CROP, CROP),
+                           mode="literal")
+            ia = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(bapi, seed=3).items()}
+            with torch.no_grad():
+                tapi = rapi.render(ia["params_target"], ia["center3d"], ia["cube"])[0].clone()
+            papi = ia["params"].clone().requires_grad_(True)
+
+            def api_step():
+                img_a = rapi.render(papi, ia["center3d"], ia["cube"])[0]
+                _m2d(tapi, img_a).backward()
+                papi.grad = None
+
+            for _ in range(5):
+                api_step()
+            t_api = time_region(api_step, 50)
+            other["drop_in_api_literal_batch%d" % bapi] = {
+                "hands": bapi, "ms_per_step": t_api, "fits_per_s": bapi / (t_api * 1e-3),
+                "note": "Render.render + m2d_loss + backward through torch autograd, eager (no CUDA graph)"}
         # config C3 (BASELINE.json configs[3]): 256x256, 3 camera views per hand, batch 512, depth + silhouette
         # (union-mask) loss through the modular autograd API: MANO once per hand, per view a rigid rotation
         # about center3d (RotationPoints), rasterise, m2d loss, backward to the 62 parameters
