@@ -228,6 +228,7 @@ def run_ours(args):
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = D.bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else False
     B = args.batch
     layer = MANO_SMPL(make_synthetic_mano(0), "nyu")
     inp = sample_fit_inputs(B, seed=1000 + rank)
@@ -511,7 +512,7 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
         "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph, "stream_chunks": args.chunks,
         "roofline": roofline, "cpu_baseline": cpu, "loss": float(step.totals[0]), "other_configs": other,
-        "e2e_%s_target" % alt_fmt: e2e_alt,
+        "e2e_%s_target" % alt_fmt: e2e_alt, "numa_bound": numa_bound,
     }
     print(json.dumps(line), flush=True)
 
@@ -529,6 +530,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=2, help="slices of the batch run on parallel streams")
     ap.add_argument("--target-format", choices=["u16", "f32"], default="u16",
                     help="how the target depth crop travels host->device in the e2e measurement")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()

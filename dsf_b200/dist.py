@@ -98,3 +98,25 @@ def max_over_ranks(value: float, device) -> float:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin the calling process to the CPU cores next to its GPU (NVML's ideal affinity) so that pinned
+    host buffers are first-touched on the GPU's own NUMA node.  With one process per GPU all pulling
+    host memory at PCIe rate, remote-node buffers are what saturates first.  Best effort: returns
+    False when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = local_rank
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
