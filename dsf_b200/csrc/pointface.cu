@@ -69,7 +69,7 @@ __device__ __forceinline__ float point_tri(V3 p, V3 v0, V3 v1, V3 v2, int* branc
 #define PF_REC 24
 // [0..2] v0  [3..5] e1=v1-v0  [6..8] e2=v2-v0  [9..11] unit normal  [12] d00 [13] d01 [14] d11
 // [15] 1/(d00 d11 - d01^2 + eps)  [16] 1/|e1|^2  [17] 1/|e2|^2  [18] 1/|v2-v1|^2  (0 = degenerate edge)
-// [19] 1 if |n| > eps
+// [19] 1 if |n| > eps  [20..22] bounding-sphere centre - v0  [23] bounding-sphere radius
 __device__ __forceinline__ void build_face_record(const float* vb, const int* faces, int f, float* r) {
     const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
     const V3 v0 = v3(vb[3 * i0], vb[3 * i0 + 1], vb[3 * i0 + 2]);
@@ -90,6 +90,21 @@ __device__ __forceinline__ void build_face_record(const float* vb, const int* fa
     r[17] = d11 <= PF_EPS ? 0.f : 1.f / d11;
     r[18] = l12 <= PF_EPS ? 0.f : 1.f / l12;
     r[19] = nn > PF_EPS ? 1.f : 0.f;
+    // Bounding sphere for the cull of the forward scan.  The reference's inside test divides by
+    // den + eps, so its barycentrics are the true ones times den / (den + eps): it accepts the plane
+    // distance t^2 for projections inside the triangle SCALED about v0 by k = (den + eps) / den.  The sphere
+    // (centroid, farthest vertex) therefore covers that scaled triangle, which contains the real one;
+    // |p - c| - r is then a lower bound of whatever distance the full test can return.  Ill-conditioned
+    // faces (den -> 0) get an unbounded radius and are never culled.
+    const float den = d00 * d11 - d01 * d01;
+    const float k = den > 1e-30f ? (den + PF_EPS) / den : INFINITY;
+    const V3 s1 = e1 * k, s2 = e2 * k;
+    const V3 cr = (s1 + s2) * (1.f / 3.f);
+    const V3 a1 = cr - s1, a2 = cr - s2;
+    const float rr = sqrtf(fmaxf(dot(cr, cr), fmaxf(dot(a1, a1), dot(a2, a2))));
+    const bool ok = k < 1e6f && rr < 1e18f;
+    r[20] = ok ? cr.x : 0.f; r[21] = ok ? cr.y : 0.f; r[22] = ok ? cr.z : 0.f;
+    r[23] = ok ? rr : 1e18f;
 }
 
 // squared distance from the point with offset a = p - origin to the segment origin + t d, t in [0,1];
@@ -100,17 +115,84 @@ __device__ __forceinline__ float seg_d2(V3 a, V3 d, float inv_l2) {
     return dot(q, q);
 }
 
+// Optional pre-pass: order the points of each hand by a 16^3 grid cell of their bounding box (counting
+// sort with shared-memory integer atomics), so that the 32 points of a warp are neighbours in space and
+// the per-face sphere test below rejects the same faces for the whole warp.  order (B,P) int32.
+#define PS_THREADS 256
+#define PS_GRID 16
+__global__ void __launch_bounds__(PS_THREADS)
+point_sort_kernel(int P, const float* __restrict__ points, int* __restrict__ order) {
+    __shared__ int s_hist[PS_GRID * PS_GRID * PS_GRID];
+    __shared__ float s_red[PS_THREADS / 32][6];
+    __shared__ int s_warp[PS_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* pp = points + (size_t)b * P * 3;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < P; i += PS_THREADS)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], pp[3 * i + k]); hi[k] = fmaxf(hi[k], pp[3 * i + k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s_red[warp][k] = lo[k]; s_red[warp][3 + k] = hi[k]; }
+    for (int i = tid; i < PS_GRID * PS_GRID * PS_GRID; i += PS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    float inv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int w = 0; w < PS_THREADS / 32; ++w) { lo[k] = fminf(lo[k], s_red[w][k]); hi[k] = fmaxf(hi[k], s_red[w][3 + k]); }
+        inv[k] = hi[k] > lo[k] ? (float)PS_GRID / (hi[k] - lo[k]) : 0.f;
+    }
+    auto cell = [&](int i) {
+        int c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int q = (int)((pp[3 * i + k] - lo[k]) * inv[k]);
+            c[k] = q < 0 ? 0 : (q > PS_GRID - 1 ? PS_GRID - 1 : q);      // NaN / inf land in a border cell
+        }
+        // boustrophedon order keeps consecutive cells adjacent
+        const int y = (c[2] & 1) ? PS_GRID - 1 - c[1] : c[1];
+        const int x = (y & 1) ? PS_GRID - 1 - c[0] : c[0];
+        return (c[2] * PS_GRID + y) * PS_GRID + x;
+    };
+    for (int i = tid; i < P; i += PS_THREADS) atomicAdd(&s_hist[cell(i)], 1);
+    __syncthreads();
+    // exclusive scan of the 4096 bins: 16 consecutive bins per thread
+    const int per = PS_GRID * PS_GRID * PS_GRID / PS_THREADS, b0 = tid * per;
+    int local = 0;
+    for (int i = 0; i < per; ++i) local += s_hist[b0 + i];
+    int incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int run = incl - local;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    for (int i = 0; i < per; ++i) { const int h = s_hist[b0 + i]; s_hist[b0 + i] = run; run += h; }
+    __syncthreads();
+    for (int i = tid; i < P; i += PS_THREADS) order[(size_t)b * P + atomicAdd(&s_hist[cell(i)], 1)] = i;
+}
+
 __global__ void __launch_bounds__(PF_THREADS)
 point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, const float* __restrict__ verts,
-                      const int* __restrict__ faces, float* __restrict__ dists, int* __restrict__ idxs) {
+                      const int* __restrict__ faces, const int* __restrict__ order, float* __restrict__ dists,
+                      int* __restrict__ idxs) {
     __shared__ __align__(16) float s_rec[PF_CHUNK * PF_REC];
     const int b = blockIdx.y;
-    const int pi = blockIdx.x * PF_THREADS + threadIdx.x;
-    const bool live = pi < P;
-    const float* pp = points + ((size_t)b * P + (live ? pi : 0)) * 3;
+    const int slot = blockIdx.x * PF_THREADS + threadIdx.x;
+    const bool live = slot < P;
+    const int pi = live ? (order ? order[(size_t)b * P + slot] : slot) : 0;
+    const float* pp = points + ((size_t)b * P + pi) * 3;
     const V3 p = v3(pp[0], pp[1], pp[2]);
     const float* vb = verts + (size_t)b * V * 3;
-    float best = INFINITY;
+    float best = INFINITY, sb = INFINITY;          // sb = sqrt(best), refreshed when best improves
     int bi = -1;
     for (int f0 = 0; f0 < F; f0 += PF_CHUNK) {
         const int nf = min(PF_CHUNK, F - f0);
@@ -119,10 +201,18 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
         __syncthreads();
         for (int f = 0; f < nf; ++f) {
             const float4* r4 = reinterpret_cast<const float4*>(s_rec + f * PF_REC);
-            const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
-            const V3 v0 = v3(q0.x, q0.y, q0.z), e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
-            const V3 nh = v3(q2.y, q2.z, q2.w);
+            const float4 q0 = r4[0], q5 = r4[5];
+            const V3 v0 = v3(q0.x, q0.y, q0.z);
             const V3 a = p - v0;                                 // point relative to v0
+            // sphere cull: the face cannot beat `best` when |p - c| >= sqrt(best) + r.  A few 1e-4 of
+            // slack keep it conservative against the rounding of either side, so the surviving minimum
+            // (and, with the strict < below, the arg-min) is the brute-force one.
+            const V3 ac = a - v3(q5.x, q5.y, q5.z);
+            const float reach = sb + q5.w;
+            if (dot(ac, ac) > reach * reach * 1.0002f + 1e-30f) continue;
+            const float4 q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+            const V3 e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
+            const V3 nh = v3(q2.y, q2.z, q2.w);
             const float t = -dot(a, nh);                         // signed plane distance (v0 - p) . n
             const V3 c = a + nh * t;                             // projection on the plane, relative to v0
             const float d20 = dot(c, e1), d21 = dot(c, e2);
@@ -138,7 +228,7 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
                 const float e12 = seg_d2(a - e1, e2 - e1, q4.z);
                 d = fminf(fminf(e01, e02), e12);
             }
-            if (d < best) { best = d; bi = f0 + f; }      // strict: lowest face index wins ties
+            if (d < best) { best = d; bi = f0 + f; sb = sqrtf(d); }      // strict: lowest face index wins ties
         }
     }
     if (live) {
@@ -222,12 +312,17 @@ point_face_bwd_kernel(int P, int V, const float* __restrict__ points, const floa
 }
 
 extern "C" int dsf_point_face_forward(int batch, int P, int V, int F, const float* points, const float* verts,
-                                      const int* faces, float* dists, int* idxs, dsfStream_t stream) {
+                                      const int* faces, float* dists, int* idxs, int* order_ws, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(points && verts && faces && dists && idxs, "null argument");
     DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0 && F > 0, "sizes");
+    if (order_ws) {
+        point_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(P, points, order_ws);
+        DSF_CHECK_LAUNCH();
+    }
     dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
-    point_face_fwd_kernel<<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, dists, idxs);
+    point_face_fwd_kernel<<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws, dists,
+                                                                       idxs);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

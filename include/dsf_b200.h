@@ -154,8 +154,11 @@ int dsf_coll_forward_backward(const DsfMano* h, int batch, const float* joints, 
  * metric/meshLoss.py:21-70 and used by ICPLoss (:347-353) / JointICPLoss (:377-394), with the
  * batch-shared face list DSF always passes.  points (B,P,3), verts (B,V,3),
  * faces (F,3) int32 device pointer -> dists (B,P) squared, idxs (B,P) face index in its mesh. */
+/* order_ws: (B,P) int32 scratch or NULL.  With it the points of each hand are first ordered by a 16^3 grid
+ * cell (one extra kernel) so that a warp's points are neighbours and the per-face bounding-sphere test
+ * culls whole warps; results are identical either way (the brute-force minimum and arg-min). */
 int dsf_point_face_forward(int batch, int P, int V, int F, const float* points, const float* verts,
-                           const int* faces, float* dists, int* idxs, dsfStream_t stream);
+                           const int* faces, float* dists, int* idxs, int* order_ws, dsfStream_t stream);
 int dsf_point_face_backward(int batch, int P, int V, int F, const float* points, const float* verts,
                             const int* faces, const int* idxs, const float* g_dists,
                             float* g_points, float* g_verts, dsfStream_t stream);
