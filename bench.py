@@ -414,7 +414,7 @@ def run_ours(args):
         pairs = b4 * P * layer.faces_int.shape[0]
         other["C4_icp_batch1024"] = {"hands": b4, "points": P, "faces": int(layer.faces_int.shape[0]),
                                      "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
-                                     "note": "brute-force ICPLoss fwd+bwd; FP32 compute bound, bytes negligible"}
+                                     "note": "ICPLoss fwd+bwd; exhaustive scan with a per-face bounding-sphere cull over spatially ordered points (rate counts all point-face pairs); FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
         # the reference's own call sequence through the drop-in classes: Render.render -> m2d loss -> backward
         # (one autograd node + the loss op), literal 640^2 -> 480x640 -> 128^2 pixel chain, batch 128 (configs[1])

@@ -155,10 +155,13 @@ point_sort_kernel(int P, const float* __restrict__ points, int* __restrict__ ord
             const int q = (int)((pp[3 * i + k] - lo[k]) * inv[k]);
             c[k] = q < 0 ? 0 : (q > PS_GRID - 1 ? PS_GRID - 1 : q);      // NaN / inf land in a border cell
         }
-        // boustrophedon order keeps consecutive cells adjacent
-        const int y = (c[2] & 1) ? PS_GRID - 1 - c[1] : c[1];
-        const int x = (y & 1) ? PS_GRID - 1 - c[0] : c[0];
-        return (c[2] * PS_GRID + y) * PS_GRID + x;
+        // Morton (Z-order) key: 32 consecutive points form a compact 3-D blob, not a strip
+        int key = 0;
+#pragma unroll
+        for (int bit = 0; bit < 4; ++bit)
+            key |= (((c[0] >> bit) & 1) << (3 * bit)) | (((c[1] >> bit) & 1) << (3 * bit + 1)) |
+                   (((c[2] >> bit) & 1) << (3 * bit + 2));
+        return key;
     };
     for (int i = tid; i < P; i += PS_THREADS) atomicAdd(&s_hist[cell(i)], 1);
     __syncthreads();
