@@ -357,8 +357,7 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 #define RT_TH 64             // tile height: 64 KB of keys -> two CTAs per SM
 #define RT_THREADS 512
 #define RT_MAXR 512
-#define RT_CAP 4096          // (items + candidates) / 2: list storage in 32-bit entries
-#define RT_WCANDS 512        // per-warp candidate list (16 warps x 512 entries = 2 * RT_CAP)
+#define RT_WCANDS 512        // per-warp candidate list, 32-bit entries (16 warps x 512 x 4 B = 32 KB)
 #define RT_MAXF 2047         // face id is packed into 11 bits
 
 struct RasterSmem {
@@ -367,7 +366,6 @@ struct RasterSmem {
     float* xs;                 // R
     float* ys;                 // R
     unsigned int* fp;          // F packed vertex ids
-    unsigned int* items;       // per-warp item lists
     unsigned int* cands;       // per-warp candidate lists
     int* counters;             // [0] next face batch
 };
@@ -379,15 +377,14 @@ __device__ __forceinline__ RasterSmem carve_smem(unsigned char* raw, int R, int 
     s.xs = s.vn + 2340;
     s.ys = s.xs + R;
     s.fp = reinterpret_cast<unsigned int*>(s.ys + R);
-    s.items = s.fp + ((F + 3) & ~3);
-    s.cands = s.items;
-    s.counters = reinterpret_cast<int*>(s.items + 2 * RT_CAP);
+    s.cands = s.fp + ((F + 3) & ~3);
+    s.counters = reinterpret_cast<int*>(s.cands + (RT_THREADS / 32) * RT_WCANDS);
     return s;
 }
 
 static size_t raster_fwd_smem(int R, int F) {
     return (size_t)RT_TW * RT_TH * 8 + 2340 * 4 + (size_t)2 * R * 4 + (size_t)((F + 3) & ~3) * 4 +
-           (size_t)2 * RT_CAP * 4 + 16;
+           (size_t)(RT_THREADS / 32) * RT_WCANDS * 4 + 16;
 }
 
 // exact evaluation of pixel (i,j) against face f, commit to the z-buffer
@@ -764,7 +761,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     }
     if (parts_tile) {
         // fixed-order block reduction (the lists are dead by now, reuse their storage)
-        float* red = reinterpret_cast<float*>(s.items);
+        float* red = reinterpret_cast<float*>(s.cands);
         l_sum = warp_sum(l_sum);
         l_cnt = warp_sum(l_cnt);
         __syncthreads();
