@@ -828,12 +828,12 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
 // perspective-correct barycentrics to the three NDC vertices (shared-memory atomics), then through
 // the projection to camera space.
 // ------------------------------------------------------------------------------------------------
-#define RB_CHUNK 16384      // pixels per pass; list entries are 16-bit offsets into the chunk
+#define RB_CHUNK 8192       // pixels per pass (16 KB list, 36 KB of shared memory per CTA); list entries are 16-bit offsets
 
 // RB_THREADS: 256 keeps more CTAs (hands) in flight for large batches, 512 halves the per-hand latency
 // when the batch does not fill the GPU anyway
 template <int RB_THREADS>
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, RB_THREADS == 256 ? 6 : 2)     // 40 registers: 6 CTAs (48 warps) per SM
 raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const int* __restrict__ faces,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
