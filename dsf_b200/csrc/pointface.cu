@@ -8,8 +8,9 @@
 #include "common.cuh"
 
 #define PF_EPS 1e-8f
-#define PF_THREADS 128
-#define PF_CHUNK 448     // faces staged per pass: 448 records * 96 B = 42 KB of shared memory
+#define PF_THREADS 256
+#define PF_CHUNK 224     // faces staged per pass: 224 records * 96 B = 21 KB of shared memory (measured best
+                         // against 448 / 160 records and 128-thread CTAs: more resident warps per SM)
 
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
