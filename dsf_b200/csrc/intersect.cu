@@ -6,7 +6,7 @@
 // part s (ray parity, forwards and backwards along a fixed direction), volume = count * pitch^3.
 //
 // Three launches per batch: (1) per hand: cap centres + part boxes in float64; (2) per (part t, hand):
-// the voxel set as a bitmap over the part's box in shared memory, then every set voxel against every
+// the voxel set as a bitmap over z-slabs of the part's box in shared memory, then every set voxel against every
 // paired part s; (3) per hand: sum of the pair counts.  All geometry is float64 like the reference;
 // the deciding arithmetic uses explicit _rn intrinsics in the oracle's operation order, so the counts
 // are integers that match oracle/intersect_oracle.c exactly.
@@ -16,7 +16,9 @@
 
 #define IV_THREADS 256
 #define IV_MAX_PARTS 32
-#define IV_BITMAP_BYTES (192 * 1024)
+#ifndef IV_BITMAP_BYTES
+#define IV_BITMAP_BYTES (24 * 1024)   // 196 k voxels per z-slab; small enough for 8 CTAs per SM
+#endif
 #define IV_MAX_LEVEL 10
 
 struct d3 { double x, y, z; };

@@ -271,7 +271,7 @@ int dsf_target_from_u16(int batch, int R, const unsigned short* depth_mm, const 
  * pair_mask[s*n_parts+t] != 0: count the surface voxels of t whose centre lies inside s.
  * Outputs: pair_counts (B,n_parts,n_parts) int64, voxel_counts (B,n_parts) int64 or NULL,
  * volume (B) float64 = sum(pair_counts) * pitch^3 (-1 if status != 0), status (B) int32 bit 0 = a
- * one z-layer of a part exceeds the voxel bitmap (1.5 M voxels; larger boxes are processed in z-slabs), bit 1 = more than 10 subdivision levels
+ * one z-layer of a part's box exceeds the voxel bitmap (196 k voxels; boxes are processed in z-slabs), bit 1 = more than 10 subdivision levels
  * (trimesh raises there).  All topology arrays and outputs are device pointers; workspace of
  * dsf_intersect_workspace_bytes() bytes, 8-byte aligned.  Geometry is evaluated in float64. */
 long dsf_intersect_workspace_bytes(int batch, int n_verts, int n_caps, int n_parts);

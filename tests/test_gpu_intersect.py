@@ -66,7 +66,7 @@ def test_intersect_status_flags():
     assert int(out["status"][0]) & 1 and float(out["volume"][0]) == -1.0      # one z-layer larger than the bitmap
     with pytest.raises(ValueError):
         self_intersection(big, topo, 1.0)
-    tiny = torch.tensor(np.concatenate([cube(0, 10), cube(0, 20)]))[None].cuda()
+    tiny = torch.tensor(np.concatenate([cube(0, 10), cube(0, 8)]))[None].cuda()
     out = intersect_counts(tiny, topo, 0.02)                                   # > 10 subdivision levels
     assert int(out["status"][0]) & 2
     with pytest.raises(ValueError):
