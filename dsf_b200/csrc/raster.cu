@@ -828,7 +828,9 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
 // perspective-correct barycentrics to the three NDC vertices (shared-memory atomics), then through
 // the projection to camera space.
 // ------------------------------------------------------------------------------------------------
-#define RB_CHUNK 8192       // pixels per pass (16 KB list, 36 KB of shared memory per CTA); list entries are 16-bit offsets
+// pixels per pass (list entries are 16-bit offsets): 8192 for the 256-thread variant (16 KB list, 36 KB of
+// shared memory per CTA, 6 CTAs per SM), 16384 for the 512-thread small-batch variant (one pass at R = 128)
+#define RB_CHUNK_OF(threads) ((threads) == 256 ? 8192 : 16384)
 
 // RB_THREADS: 256 keeps more CTAs (hands) in flight for large batches, 512 halves the per-hand latency
 // when the batch does not fill the GPU anyway
@@ -893,6 +895,7 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     __shared__ int s_count;
     const int lane = tid & 31;
     const int n_pix = R * R;
+    constexpr int RB_CHUNK = RB_CHUNK_OF(RB_THREADS);
     for (int chunk0 = 0; chunk0 < n_pix; chunk0 += RB_CHUNK) {
       const int chunk_n = min(RB_CHUNK, n_pix - chunk0);
       if (tid == 0) s_count = 0;
@@ -1010,8 +1013,9 @@ int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, c
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
                              const float* img, const float* parts, float gscale, float thr, const CropParams* crop,
                              cudaStream_t st) {
-    const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK * 2;
-    const int max_smem = (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK * 2);
+    const int rb_threads = n_mesh < 2048 ? 512 : 256;
+    const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK_OF(rb_threads) * 2;
+    const int max_smem = (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK_OF(512) * 2);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
