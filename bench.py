@@ -473,7 +473,18 @@ def run_ours(args):
             "hands": b3, "views": V3, "crop": R3, "ms_fwd_bwd": t_c3, "fits_per_s": b3 / (t_c3 * 1e-3),
             "step_hbm_frac": c3_bytes * b3 / (t_c3 * 1e-3) / 1e9 / peak,
             "note": "modular autograd path (image returned, loss as a separate kernel, torch ops for the view rotation)"}
-        del tgt3, rnd3
+        # the same configuration through the fused multi-view step (dsf_fit_step_views, CUDA-graph replay)
+        from dsf_b200.fit import MultiViewFitStep
+        mv = MultiViewFitStep(layer, b3, V3, R3, use_graph=not args.no_graph)
+        mv.set_inputs(i3["params"], i3["center3d"], i3["cube"], rot3.reshape(b3, V3, 3), tgt3[:, 0])
+        for _ in range(3):
+            mv.step()
+        t_mv = time_region(mv.step, 10)
+        other["C3_multiview_256_batch512"]["fused_ms"] = t_mv
+        other["C3_multiview_256_batch512"]["fused_fits_per_s"] = b3 / (t_mv * 1e-3)
+        other["C3_multiview_256_batch512"]["fused_step_hbm_frac"] = c3_bytes * b3 / (t_mv * 1e-3) / 1e9 / peak
+        other["C3_multiview_256_batch512"]["fused_launches_per_step"] = mv.launches_per_step
+        del tgt3, rnd3, mv
         # "next" rows: depth crop -> 2048-point cloud (Img2pcl) and the intersection-volume metric (I1)
         from dsf_b200.intersection import PartTopology, intersect_counts
         from dsf_b200.pcl import Img2pcl

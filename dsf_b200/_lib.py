@@ -74,6 +74,9 @@ SIGNATURES = {
     "dsf_fit_workspace_floats": (_L, [_I, _I]),
     "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I, _VP, _I, _VP, c_float_p,
                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_fit_views_workspace_floats": (C.c_long, [_I, _I, _I]),
+    "dsf_fit_step_views": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _VP,
+                                _VP, _VP, _VP, _VP]),
     "dsf_render_workspace_floats": (C.c_long, [_I]),
     "dsf_render_forward": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, c_float_p, _VP, _VP, _VP, _VP,
                                 _VP, _VP, _VP, _VP, _VP]),

@@ -242,3 +242,93 @@ extern "C" int dsf_render_backward(const DsfMano* h, int batch, int R, const flo
     DSF_CHECK_LAUNCH();
     return dsf_mano_backward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, g_verts, g_joints, &g, workspace, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Multi-view fitting step (BASELINE config "high-res multi-view"): MANO once per hand, then per view a
+// rigid rotation about the hand's centre (RotationPoints, mano_layer.py:874-885, as getDepth does with
+// `rot`, :1204-1209), rasterise + fused m2d loss against that view's target, and the adjoint chain back to
+// the hand's 62 parameters (the views' vertex cotangents are rotated back and summed).
+// ------------------------------------------------------------------------------------------------
+// verts_cam[b, v] = R[b, v] (verts[b] * cube[b] / 2) + center[b]     (rotation about center[b])
+__global__ void __launch_bounds__(AUX_THREADS)
+views_place_kernel(int views, const float* __restrict__ verts, const float* __restrict__ center,
+                   const float* __restrict__ cube, const float* __restrict__ rot, float* __restrict__ verts_cam) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float hx = cube[3 * b] * 0.5f, hy = cube[3 * b + 1] * 0.5f, hz = cube[3 * b + 2] * 0.5f;
+    const float cx = center[3 * b], cy = center[3 * b + 1], cz = center[3 * b + 2];
+    for (int i = tid; i < NVW; i += AUX_THREADS) {
+        const float* p = verts + ((size_t)b * NVW + i) * 3;
+        const float x = p[0] * hx, y = p[1] * hy, z = p[2] * hz;
+        for (int v = 0; v < views; ++v) {
+            const float* R = rot + ((size_t)b * views + v) * 9;
+            float* o = verts_cam + (((size_t)b * views + v) * NVW + i) * 3;
+            o[0] = (R[0] * x + R[1] * y + R[2] * z) + cx;
+            o[1] = (R[3] * x + R[4] * y + R[5] * z) + cy;
+            o[2] = (R[6] * x + R[7] * y + R[8] * z) + cz;
+        }
+    }
+}
+
+// g_verts[b] = sum_v R[b, v]^T g_cam[b, v] * cube[b] / 2
+__global__ void __launch_bounds__(AUX_THREADS)
+views_place_bwd_kernel(int views, const float* __restrict__ g_cam, const float* __restrict__ cube,
+                       const float* __restrict__ rot, float* __restrict__ g_verts) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float hx = cube[3 * b] * 0.5f, hy = cube[3 * b + 1] * 0.5f, hz = cube[3 * b + 2] * 0.5f;
+    for (int i = tid; i < NVW; i += AUX_THREADS) {
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        for (int v = 0; v < views; ++v) {                       // fixed order: deterministic sum
+            const float* R = rot + ((size_t)b * views + v) * 9;
+            const float* g = g_cam + (((size_t)b * views + v) * NVW + i) * 3;
+            ax += R[0] * g[0] + R[3] * g[1] + R[6] * g[2];
+            ay += R[1] * g[0] + R[4] * g[1] + R[7] * g[2];
+            az += R[2] * g[0] + R[5] * g[1] + R[8] * g[2];
+        }
+        float* o = g_verts + ((size_t)b * NVW + i) * 3;
+        o[0] = ax * hx; o[1] = ay * hy; o[2] = az * hz;
+    }
+}
+
+extern "C" long dsf_fit_views_workspace_floats(int batch, int views, int R) {
+    const long nm = (long)batch * views;
+    return (long)batch * (WS_PER_HAND + NVW * 3) + nm * (2L * NVW * 3 + 2L * dsf_raster_tiles(R));
+}
+
+extern "C" int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R, const float* params,
+                                  const float* center3d, const float* cube, const float* rot, const float* view,
+                                  const float* xs, const float* ys, const float* target, float loss_weight,
+                                  float* img, int* pix_to_face, float* verts, float* joints, float* g_params,
+                                  float* parts, float* totals, float* workspace, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && params && center3d && cube && rot && view && xs && ys && target, "null input");
+    DSF_REQUIRE(img && pix_to_face && verts && joints && g_params && parts && totals && workspace, "null output");
+    DSF_REQUIRE(batch > 0 && views > 0 && (long)batch * views <= 65535, "batch * views must be in [1,65535] per call");
+    DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nm = batch * views, n_tiles = dsf_raster_tiles(R);
+    float* ws_mano = workspace;
+    float* g_verts = workspace + (size_t)batch * WS_PER_HAND;
+    float* verts_cam = g_verts + (size_t)batch * NVW * 3;
+    float* g_cam = verts_cam + (size_t)nm * NVW * 3;
+    float* parts_tile = g_cam + (size_t)nm * NVW * 3;
+    const float thr = 0.99f;
+    DsfManoParams p;
+    DsfManoGrads g;
+    render_params(params, 62, 3, g_params, &p, &g);
+    const float unit_scale = 1000.f * (1.f / 125.f);
+    int rc = dsf_mano_forward_impl(h, batch, &p, unit_scale, verts, joints, nullptr, ws_mano, st);
+    if (rc) return rc;
+    views_place_kernel<<<batch, AUX_THREADS, 0, st>>>(views, verts, center3d, cube, rot, verts_cam);
+    DSF_CHECK_LAUNCH();
+    rc = dsf_raster_forward_impl(h, nm, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face, nullptr, nullptr,
+                                 nullptr, target, thr, parts_tile, nullptr, st);
+    if (rc) return rc;
+    rc = dsf_fold_loss_impl(nm, n_tiles, loss_weight, parts_tile, parts, totals, st);
+    if (rc) return rc;
+    rc = dsf_raster_backward_impl(h, nm, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face, nullptr, g_cam, target,
+                                  img, parts, loss_weight / (float)nm, thr, nullptr, st);
+    if (rc) return rc;
+    views_place_bwd_kernel<<<batch, AUX_THREADS, 0, st>>>(views, g_cam, cube, rot, g_verts);
+    DSF_CHECK_LAUNCH();
+    return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
+}

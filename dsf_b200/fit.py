@@ -145,3 +145,88 @@ class FitStep:
         self._enqueue()
         self.target.copy_(self.img)
         self.params.copy_(keep)
+
+
+class MultiViewFitStep:
+    """Fused multi-view fitting step (dsf_fit_step_views): MANO once per hand, V rigidly rotated views per
+    hand (RotationPoints about center3d, the reference's `getDepth(..., rot)` pattern), one depth +
+    silhouette (union-mask m2d) loss over all B*V images and the summed adjoint back to the 62 parameters.
+    Buffers are persistent; the launch sequence is replayed as a CUDA graph."""
+
+    def __init__(self, mano_layer, batch, views, crop=256, cam_para=(588.03, 587.07, 320.0, 240.0),
+                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None):
+        self.lib = L.lib()
+        self.layer = mano_layer
+        self.B, self.V, self.R = int(batch), int(views), int(crop)
+        self.mode = 0 if mode == "direct" else 1
+        self.loss_weight = float(loss_weight)
+        self.dev = device or mano_layer.v_template.device
+        self.W, self.H = int(image_size[0]), int(image_size[1])
+        self._intr = (C.c_float * 4)(*[float(v) for v in cam_para])
+        B, V, R, dev = self.B, self.V, self.R, self.dev
+        f = lambda *s: torch.empty(*s, device=dev)
+        self.params, self.center3d, self.cube = f(B, 62), f(B, 3), f(B, 3)
+        self.rot = f(B, V, 3, 3)
+        self.target = f(B * V, R, R)
+        self.view, self.xs, self.ys, self.M = f(B * V, L.VIEW_STRIDE), f(B * V, R), f(B * V, R), f(B * V, 3, 3)
+        self._c3v, self._cubev = f(B * V, 3), f(B * V, 3)
+        self.img = f(B * V, R, R)
+        self.p2f = torch.empty(B * V, R, R, dtype=torch.int32, device=dev)
+        self.verts, self.joints = f(B, L.NVW, 3), f(B, L.NJOUT, 3)
+        self.g_params = f(B, 62)
+        self.parts, self.totals = f(B * V, 2), f(4)
+        self.ws = f(self.lib.dsf_fit_views_workspace_floats(B, V, R))
+        self.use_graph = use_graph
+        self._graph = None
+        self.launches_per_step = 0
+
+    def set_inputs(self, params, center3d, cube, rot, target=None):
+        """rot: (B,V,3) axis-angle or (B,V,3,3) rotation matrices of the views about center3d."""
+        from .mano_layer import batch_rodrigues
+
+        self.params.copy_(params, non_blocking=True)
+        self.center3d.copy_(center3d, non_blocking=True)
+        self.cube.copy_(cube, non_blocking=True)
+        rot = rot.to(self.dev)
+        if rot.dim() == 3:
+            rot = batch_rodrigues(rot.reshape(-1, 3)).reshape(self.B, self.V, 3, 3)
+        self.rot.copy_(rot)
+        self._c3v.copy_(self.center3d.repeat_interleave(self.V, 0))
+        self._cubev.copy_(self.cube.repeat_interleave(self.V, 0))
+        if target is not None:
+            self.target.copy_(target.reshape(self.B * self.V, self.R, self.R), non_blocking=True)
+
+    def _enqueue(self):
+        s = L.stream_ptr()
+        L.check(self.lib.dsf_view_setup(self.mode, self.B * self.V, self._c3v.data_ptr(), self._cubev.data_ptr(),
+                                        self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
+                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), s))
+        n = self.lib.dsf_last_launch_count()
+        L.check(self.lib.dsf_fit_step_views(
+            self.layer._handle, self.B, self.V, self.R, self.params.data_ptr(), self.center3d.data_ptr(),
+            self.cube.data_ptr(), self.rot.data_ptr(), self.view.data_ptr(), self.xs.data_ptr(), self.ys.data_ptr(),
+            self.target.data_ptr(), self.loss_weight, self.img.data_ptr(), self.p2f.data_ptr(), self.verts.data_ptr(),
+            self.joints.data_ptr(), self.g_params.data_ptr(), self.parts.data_ptr(), self.totals.data_ptr(),
+            self.ws.data_ptr(), s))
+        self.launches_per_step = n + self.lib.dsf_last_launch_count()
+
+    def step(self):
+        if not self.use_graph:
+            self._enqueue()
+            return
+        if self._graph is None:
+            self._enqueue()
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self._graph = g
+        self._graph.replay()
+
+    def render_target(self, params_target):
+        keep = self.params.clone()
+        self.params.copy_(params_target)
+        self.target.fill_(1.0)
+        self._enqueue()
+        self.target.copy_(self.img)
+        self.params.copy_(keep)

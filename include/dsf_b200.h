@@ -206,6 +206,19 @@ int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const 
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
                  float* workspace, dsfStream_t stream);
 
+/* Multi-view fused step (BASELINE config "high-res multi-view"): MANO once per hand; per view v the posed
+ * hand is rotated about center3d[b] by rot[b, v] (3x3 row-major; RotationPoints :874-885 as getDepth uses it,
+ * :1204-1209), rasterised with that view's record (view / xs / ys for batch * views meshes, view-minor) and
+ * compared with target (batch * views, R, R) by the union-mask m2d loss (depth + silhouette), mean over all
+ * batch * views images times loss_weight; the adjoints of all views are summed into g_params (B,62).
+ * img / pix_to_face (batch * views, R, R), parts (batch * views, 2), totals (4) as in dsf_fit_step. */
+long dsf_fit_views_workspace_floats(int batch, int views, int R);
+int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R, const float* params,
+                       const float* center3d, const float* cube, const float* rot, const float* view,
+                       const float* xs, const float* ys, const float* target, float loss_weight,
+                       float* img, int* pix_to_face, float* verts, float* joints, float* g_params,
+                       float* parts, float* totals, float* workspace, dsfStream_t stream);
+
 /* R5 - Render.render (render_model/mano_layer.py:1071-1097) as one forward and one backward call for the
  * autograd drop-in: params (B, ld_params >= 62 | 63) = [quat(3|4) | theta45 | beta10 | scale, trans3],
  * view / xs / ys / M from dsf_view_setup.  Outputs: img (B,R,R) normalised depth, pix_to_face (B,R,R),
