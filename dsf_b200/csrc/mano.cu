@@ -355,7 +355,7 @@ int dsf_blend_backward_splits(int M);
 // K3: skinning kernel - one CTA per hand.  LBS (:619-629), joint regression (:630-633), wrist-cap
 // vertex (:636-637), unit / camera scaling (:662-675).
 // ------------------------------------------------------------------------------------------------
-#define SKIN_T 128
+#define SKIN_T 256
 static const int h_tips[5] = {333, 444, 672, 555, 744};
 __constant__ int c_ring[16];
 __constant__ int c_tips[5];
@@ -458,7 +458,7 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ 
 // Kb2: skinning backward - one CTA per hand.
 //   cotangents of verts/joints -> g_vposed (ws), g_A (ws), g_cam.
 // ------------------------------------------------------------------------------------------------
-#define SKB_T 128
+#define SKB_T 256
 
 __global__ void __launch_bounds__(SKB_T)
 mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
