@@ -96,9 +96,12 @@ __device__ __forceinline__ void build_face_record(const float* vb, const int* fa
     // distance t^2 for projections inside the triangle SCALED about v0 by k = (den + eps) / den.  The sphere
     // (centroid, farthest vertex) therefore covers that scaled triangle, which contains the real one;
     // |p - c| - r is then a lower bound of whatever distance the full test can return.  Ill-conditioned
-    // faces (den -> 0) get an unbounded radius and are never culled.
+    // faces (den -> 0, or den lost in its rounding noise) get an unbounded radius and are never culled.
+    // den = |e1|^2 |e2|^2 sin^2(angle) is only trusted when it stands clear of its own rounding noise
+    // (about 1e-7 d00 d11): below a 0.6 degree corner angle the fp32 barycentrics of the reference are noise
+    // themselves and the face is never culled; above it 1 % of slack on k covers the remaining error.
     const float den = d00 * d11 - d01 * d01;
-    const float k = den > 1e-30f ? (den + PF_EPS) / den : INFINITY;
+    const float k = den > 1e-4f * d00 * d11 && den > 1e-30f ? 1.01f * (den + PF_EPS) / den : INFINITY;
     const V3 s1 = e1 * k, s2 = e2 * k;
     const V3 cr = (s1 + s2) * (1.f / 3.f);
     const V3 a1 = cr - s1, a2 = cr - s2;

@@ -160,3 +160,37 @@ def test_point_face_against_brute_force(mano_model):
             pm[0, ax] -= h
             fd = (dist64(pp) - dist64(pm)) / (2 * h)
             assert abs(fd - gp[0, i, ax].item()) <= 1e-3 * max(1.0, abs(fd))
+
+
+def test_point_face_sphere_bound_never_exceeds_reported_distance():
+    """The cull of dsf_point_face_forward skips a face when |p - c| >= sqrt(best) + r, with the sphere built
+    over the triangle scaled about v0 by (den + eps) / den (the region where the eps-regularised inside test of
+    the reference returns the plane distance).  Checked here against the oracle's reported distance on random,
+    small and ill-conditioned triangles: (|p - c| - r)^2 must never exceed it (0.02 % slack as in the kernel)."""
+    from oracle import raster_oracle as ro
+
+    gen = torch.Generator().manual_seed(11)
+    T, P = 4000, 64
+    scale = 10 ** (torch.rand(T, 1, 1, generator=gen) * 3 - 3)               # edge lengths 1e-3 .. 1
+    tri = torch.randn(T, 3, 3, generator=gen) * scale
+    tri[::7, 2] = tri[::7, 0] + (tri[::7, 1] - tri[::7, 0]) * 0.4 + 1e-6 * torch.randn(len(tri[::7]), 3, generator=gen)  # slivers
+    tri = tri + torch.randn(T, 1, 3, generator=gen)
+    pts = tri.mean(1, keepdim=True) + torch.randn(T, P, 3, generator=gen) * scale * 10 ** (torch.rand(T, P, 1, generator=gen) * 3 - 2)
+    faces = torch.tensor([[0, 1, 2]], dtype=torch.int32)
+    d, _ = ro.point_face(pts.contiguous(), tri.contiguous(), faces)
+    v0, e1, e2 = tri[:, 0], tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    d00, d01, d11 = (e1 * e1).sum(-1), (e1 * e2).sum(-1), (e2 * e2).sum(-1)
+    den = d00 * d11 - d01 * d01
+    k = torch.where((den > 1e-4 * d00 * d11) & (den > 1e-30), 1.01 * (den + 1e-8) / den, torch.full_like(den, float("inf")))
+    s1, s2 = e1 * k[:, None], e2 * k[:, None]
+    cr = (s1 + s2) / 3
+    rr = torch.stack([cr.norm(dim=-1), (cr - s1).norm(dim=-1), (cr - s2).norm(dim=-1)]).max(0)[0]
+    ok = (k < 1e6) & (rr < 1e18)
+    assert ok.float().mean() > 0.6 and (~ok).sum() > 10                        # both branches are exercised
+    dist_c = (pts - (v0 + cr)[:, None]).norm(dim=-1)
+    lb = (dist_c - rr[:, None]).clamp(min=0) ** 2
+    viol = (lb > d * 1.0002 + 1e-30) & ok[:, None]
+    assert viol.sum() == 0, (viol.sum(), (lb / d)[viol].max())
+    # and the bound is useful: it exceeds a tenth of the distance for most far points
+    far = ok[:, None] & (dist_c > 4 * rr[:, None])
+    assert (lb[far] > 0.1 * d[far]).float().mean() > 0.9
