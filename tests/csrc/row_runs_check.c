@@ -38,6 +38,8 @@ long check(int R, long n_tri, uint64_t seed, int ulp_shift, long* n_exact, long*
         if (kind == 2) { x[2] = (float)(x[0] + (x[1] - x[0]) * 0.5 + (urand() - 0.5) * 1e-5 * size);   /* sliver */
                          y[2] = (float)(y[0] + (y[1] - y[0]) * 0.5 + (urand() - 0.5) * 1e-5 * size); }
         if (kind == 3) y[1] = y[0];                                                /* exactly horizontal edge */
+        if (kind == 4) { x[1] = (float)(cx + (urand() - 0.5) * 2000.0 * urand());   /* a vertex far outside the image */
+                         y[1] = (float)(cy + (urand() - 0.5) * 2000.0 * urand()); }
         const float x0 = x[0], y0 = y[0], x1 = x[1], y1 = y[1], x2 = x[2], y2 = y[2];
         const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
         if (farea <= 1e-8f && farea >= -1e-8f) continue;                            /* culled like the kernel */
