@@ -5,9 +5,10 @@
 
 One step = one pass of the hot path over one batch of synthetic hands: MANO forward ->
 depth rasterisation (128x128) -> m2d depth loss -> backward to the 62 MANO/camera parameters.
-Workload: BASELINE.json configs[2] ("large-batch render-loss fwd/bwd: batch 4096, 128x128"), 4096
-hands per GPU; under torchrun every rank owns its own 4096 hands (weak scaling, no data-path
-collective; one 16-byte all-reduce of the packed loss record per step).
+Workload: BASELINE.json configs[2] ("large-batch render-loss fwd/bwd: batch 4096, 128x128, batch-sharded
+across 1/2/4/8 B200"): ONE 4096-hand batch; under torchrun rank r owns the contiguous shard
+dist.shard_bounds(4096, N, r) (strong scaling, no data-path collective; one 16-byte all-reduce of the packed
+loss record per step).  The weak-scaling figure (4096 hands on every rank) is reported next to it.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -31,9 +32,11 @@ UNIT = "fits/s"
 CROP = 128
 # algorithmic bytes per hand-fit at R=128, 1 view
 BYTES_PER_FIT = 2 * CROP * CROP * 4 + 779 * 3 * 4 + 21 * 3 * 4 + 62 * 4 + 62 * 4 + 4 + 60   # 141 232
-# the rasteriser kernel as launched in the fused step: reads verts + view/sample grids + the target
-# image, writes normalised depth + pix_to_face + per-tile loss partial sums
-RASTER_BYTES_PER_HAND = 779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 3 * CROP * CROP * 4 + 16
+# the rasteriser stage of that accounting (target in, rendered depth out, vertices + camera in)
+RASTER_ALG_BYTES_PER_HAND = 2 * CROP * CROP * 4 + 779 * 3 * 4 + 60                                  # 140 480
+# bytes the fused raster launch really moves per hand: verts + view record + sample grids + target in;
+# normalised depth + two per-tile vertex-gradient shares + per-tile loss sums / flags out (no pix_to_face plane)
+RASTER_MOVED_BYTES_PER_HAND = 779 * 3 * 4 + 20 * 4 + 2 * CROP * 4 + 24 + 2 * CROP * CROP * 4 + 2 * 779 * 3 * 4 + 24
 
 
 def measured_peaks():
@@ -128,8 +131,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -138,14 +141,19 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    per = -(-args.batch // world)
+    img_mb = 2 * per * CROP * CROP * 4 / 1e6
     return {
-        "workload": f"BASELINE.json configs[2]: large-batch render-loss fwd/bwd, {args.batch} hands per GPU, "
-                    f"128x128 depth, direct crop raster, NYU intrinsics, synthetic hand-shaped MANO (778v/1554f)",
-        "hands_per_gpu": args.batch, "global_batch": args.batch * world, "crop": CROP, "views": 1,
+        "workload": f"BASELINE.json configs[2]: large-batch render-loss fwd/bwd, one {args.batch}-hand batch sharded "
+                    f"over {world} GPU(s), 128x128 depth, direct crop raster, NYU intrinsics, synthetic hand-shaped "
+                    f"MANO (778v/1554f), pytorch3d-0.4.0 rasteriser settings (perspective_correct=False)",
+        "hands_per_gpu": per, "global_batch": args.batch, "crop": CROP, "views": 1,
         "parallelism": f"batch-sharded x{world}",
         "target": "rendering of a perturbed parameter set, quantised to integer millimetres like sensor depth",
-        "l2_policy": "inputs larger than L2 (target+rendered images %.0f MB per step vs 126 MB L2)"
-                     % (2 * args.batch * CROP * CROP * 4 / 1e6),
+        "l2_policy": ("inputs larger than L2 (target+rendered images %.0f MB per step vs 126 MB L2)" % img_mb)
+                     if img_mb > 126 else
+                     ("an L2 flush (write of a 256 MB buffer) between timed steps: the shard's images (%.0f MB) "
+                      "would fit the 126 MB L2" % img_mb),
     }
 
 
@@ -172,34 +180,41 @@ def stage_times(step, iters=10):
     lib = L.lib()
     B, R, h = step.B, step.R, step.layer._handle
     s = L.stream_ptr()
-    ws = step.ws[0]
-    g_img = torch.zeros(B, R, R, device=step.dev)
-    g_verts = torch.zeros(B, 779, 3, device=step.dev)
+    dev = step.dev
+    g_img = torch.zeros(B, R, R, device=dev)
+    g_verts = torch.zeros(B, 779, 3, device=dev)
+    p2f = torch.empty(B, R, R, dtype=torch.int32, device=dev)
     vcam = (step.verts * step.cube[:, None] / 2 + step.center3d[:, None]).contiguous()
     prm = step.params
     p = L.DsfManoParams(prm.data_ptr(), 62, 3, prm.data_ptr() + 12, 62, 45, prm.data_ptr() + 192, 62,
                         prm.data_ptr() + 232, 62)
     gp = step.g_params
     g = L.DsfManoGrads(gp.data_ptr(), 62, gp.data_ptr() + 12, 62, gp.data_ptr() + 192, 62, gp.data_ptr() + 232, 62)
-    mws = torch.empty(lib.dsf_mano_workspace_floats(B), device=step.dev)
-    parts_tile = torch.empty(B * lib.dsf_raster_tiles(R) * 2, device=step.dev)
+    mws = torch.empty(lib.dsf_mano_workspace_floats(B), device=dev)
+    rws = torch.empty(lib.dsf_raster_loss_workspace_floats(B, R), device=dev)
+    parts, totals = torch.empty(B, 2, device=dev), torch.empty(4, device=dev)
     stages = {
         "mano_forward(3 kernels)": lambda: L.check(lib.dsf_mano_forward(
             h, B, C.byref(p), 8.0, step.verts.data_ptr(), step.joints.data_ptr(), None, mws.data_ptr(), s)),
-        # the rasteriser exactly as the fused step launches it: target in, loss partial sums out
-        "raster_fwd_kernel": lambda: L.check(lib.dsf_raster_forward(
+        # the rasteriser exactly as the fused step launches it: target in; depth, loss sums / totals and the
+        # per-tile vertex-gradient shares out (forward + loss + raster backward in one launch)
+        "raster_fwd_kernel[fused: +loss +vertex gradient]": lambda: L.check(lib.dsf_raster_loss_grad(
             h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
-            step.img.data_ptr(), step.p2f.data_ptr(), None, None, None, step.target.data_ptr(), 0.99,
-            parts_tile.data_ptr(), s)),
-        "depth_loss(2 kernels, modular path only)": lambda: L.check(lib.dsf_depth_loss(
-            0, B, R, step.target.data_ptr(), step.img.data_ptr(), 0.99, 0.1, step.parts.data_ptr(),
-            step.totals.data_ptr(), g_img.data_ptr(), s)),
-        "raster_bwd_kernel": lambda: L.check(lib.dsf_raster_backward(
-            h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
-            step.p2f.data_ptr(), g_img.data_ptr(), g_verts.data_ptr(), s)),
+            step.target.data_ptr(), 0.99, 0.1, B, step.img.data_ptr(), None, parts.data_ptr(), totals.data_ptr(),
+            None, rws.data_ptr(), 0, s)),
         "mano_backward(3 kernels)": lambda: L.check(lib.dsf_mano_backward(
             h, B, C.byref(p), 8.0, step.verts.data_ptr(), step.joints.data_ptr(), g_verts.data_ptr(), None,
             C.byref(g), mws.data_ptr(), s)),
+        # the modular (autograd drop-in) path's kernels, not part of the fused step
+        "modular: raster_fwd_kernel (image + pix_to_face)": lambda: L.check(lib.dsf_raster_forward(
+            h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
+            step.img.data_ptr(), p2f.data_ptr(), None, None, None, None, 0.99, None, 0, s)),
+        "modular: depth_loss (2 kernels)": lambda: L.check(lib.dsf_depth_loss(
+            0, B, R, step.target.data_ptr(), step.img.data_ptr(), 0.99, 0.1, parts.data_ptr(),
+            totals.data_ptr(), g_img.data_ptr(), s)),
+        "modular: raster_bwd_kernel": lambda: L.check(lib.dsf_raster_backward(
+            h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
+            p2f.data_ptr(), g_img.data_ptr(), g_verts.data_ptr(), 0, s)),
     }
     out = {}
     for name, fn in stages.items():
@@ -208,13 +223,46 @@ def stage_times(step, iters=10):
     # Fragments-materialising mode (SURVEY 8d accounting F): the rasteriser also writes the barycentrics
     # (3 x fp32 per pixel) next to depth and pix_to_face - the full "z-buffer + pix_to_face + barycentrics"
     # product of north_star piece (2).  Bytes really moved: 20 B/pixel out + the mesh in.
-    bary = torch.empty(B, R, R, 3, device=step.dev)
+    bary = torch.empty(B, R, R, 3, device=dev)
     frag = lambda: L.check(lib.dsf_raster_forward(
         h, B, vcam.data_ptr(), step.view.data_ptr(), step.xs.data_ptr(), step.ys.data_ptr(), R,
-        step.img.data_ptr(), step.p2f.data_ptr(), None, bary.data_ptr(), None, None, 0.99, None, s))
+        step.img.data_ptr(), p2f.data_ptr(), None, bary.data_ptr(), None, None, 0.99, None, 0, s))
     frag()
-    out["raster_fwd_kernel[fragments mode: +barycentrics]"] = time_region(frag, iters)
+    out["modular: raster_fwd_kernel[fragments mode: +barycentrics]"] = time_region(frag, iters)
     return out
+
+
+FUSED_KEY = "raster_fwd_kernel[fused: +loss +vertex gradient]"
+FRAG_KEY = "modular: raster_fwd_kernel[fragments mode: +barycentrics]"
+L2_BYTES = 126e6
+
+
+class L2Flusher:
+    """writes a buffer larger than L2 (timing rule: no warm-cache numbers for inputs that would fit L2)"""
+
+    def __init__(self, dev):
+        self.buf = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB
+
+    def __call__(self):
+        self.buf.fill_(1.0)
+
+
+def timed_steps(fn, steps, flush=None):
+    """ms per step on the device: back to back when the working set exceeds L2, else one event pair per step
+    with an L2 flush (outside the events) in between."""
+    if flush is None:
+        return time_region(fn, steps)
+    total = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(steps):
+        flush()
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / steps
 
 
 def run_ours(args):
@@ -229,11 +277,16 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_bound = D.bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else False
-    B = args.batch
+    G = args.batch                                  # the global batch (BASELINE configs[2]: 4096)
+    lo, hi = D.shard_bounds(G, rank, world)
+    B = hi - lo                                     # this rank's shard
     layer = MANO_SMPL(make_synthetic_mano(0), "nyu")
-    inp = sample_fit_inputs(B, seed=1000 + rank)
-    host = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
-    step = FitStep(layer, B, CROP, use_graph=not args.no_graph, chunks=args.chunks)
+    inp_all = sample_fit_inputs(G, seed=1000)       # every rank draws the same batch and keeps its shard
+    inp = {k: v[lo:hi] for k, v in inp_all.items()}
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in inp.items()}
+    n_chunks = lambda b: args.chunks if args.chunks > 0 else (2 if b >= 2048 else 1)
+    mk = lambda b: FitStep(layer, b, CROP, use_graph=not args.no_graph, chunks=n_chunks(b), keep_pix_to_face=False)
+    step = mk(B)
     step.set_inputs(host["params"].to(dev), host["center3d"].to(dev), host["cube"].to(dev))
     step.render_target(host["params_target"].to(dev))
     # the target is what a depth sensor delivers: integer millimetres.  It is resident (normalised fp32) for
@@ -244,7 +297,8 @@ def run_ours(args):
     step.set_inputs(step.params, step.center3d, step.cube, mm)
     torch.cuda.synchronize()
     host_targets = {"u16": mm.cpu().pin_memory(), "f32": step.target.cpu().pin_memory()}
-    reducer = D.TotalsReducer(dev, B * world)
+    reducer = D.TotalsReducer(dev, G)
+    flush = L2Flusher(dev) if 2 * B * CROP * CROP * 4 <= L2_BYTES else None
 
     def one_step():
         step.step()
@@ -257,29 +311,53 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
     with ClockSampler(local) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            one_step()
+        ms = timed_steps(one_step, args.steps, flush)
         if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             reducer.finish()                       # the last collective is inside the timed region
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1) / args.steps
         if args.steps * ms < 1500:      # keep the sampler alive long enough to see clocks under load
             time_region(step.step, int(1500 / max(ms, 1e-3)) + 1)    # local work only: no collective
     if world > 1:
         torch.distributed.barrier()
     ms = D.max_over_ranks(ms, dev)
-    value = B * world / (ms * 1e-3)
+    value = G / (ms * 1e-3)
     launches = step.launches_per_step * args.steps
+
+    # weak-scaling companion (round-1 headline): every rank owns a full 4096-hand batch
+    weak = None
+    if world > 1 and not args.no_weak:
+        wstep = mk(G)
+        wi = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(G, seed=1000 + rank).items()}
+        wstep.set_inputs(wi["params"], wi["center3d"], wi["cube"])
+        wstep.render_target(wi["params_target"])
+        wred = D.TotalsReducer(dev, G * world)
+
+        def wone():
+            wstep.step()
+            wred.submit(wstep.totals)
+
+        for _ in range(3):
+            wone()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        wms = time_region(wone, args.steps)
+        wred.finish()
+        torch.cuda.synchronize()
+        wms = D.max_over_ranks(wms, dev)
+        weak = {"hands_per_gpu": G, "global_batch": G * world, "ms_per_step": wms, "value": G * world / (wms * 1e-3),
+                "unit": UNIT, "scaling": "weak"}
+        del wstep, wi
 
     # ---- end to end through the public call with HOST buffers -------------------------------------
     # every step: H2D of that step's inputs (params, centre, cube, target depth) from pinned memory,
     # the fused step, D2H of loss + parameter gradients.  Two FitStep instances ping-pong so the copy
     # of step i+1 (copy stream) overlaps the compute of step i; all copies stay inside the timed region.
-    steps2 = [step, FitStep(layer, B, CROP, use_graph=not args.no_graph, chunks=args.chunks)]
+    steps2 = [step, mk(B)]
     h_g = [torch.empty(B, 62).pin_memory() for _ in range(2)]
     h_tot = [torch.empty(4).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
@@ -330,7 +408,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         t = D.max_over_ranks(e0.elapsed_time(e1) / e2e_iters, dev)
         h2d = B * (62 + 3 + 3) * 4 + B * CROP * CROP * (2 if fmt == "u16" else 4)
-        return {"value": B * world / (t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+        return {"value": G / (t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "ms_per_step": t, "target_format": fmt,
                 "note": "double-buffered: H2D of step i+1 overlaps compute of step i; PCIe-bound (%.0f MB in per "
                         "step); target crop travels as %s" % (h2d / 1e6, "the sensor's uint16 mm, normalised on the "
@@ -339,16 +417,21 @@ def run_ours(args):
     e2e = measure_e2e(args.target_format)
     alt_fmt = "f32" if args.target_format == "u16" else "u16"
     e2e_alt = measure_e2e(alt_fmt)
+    # both hand-offs belong next to each other: the reference uploads the loader-normalised fp32 crop
+    f32_v = (e2e if args.target_format == "f32" else e2e_alt)["value"]
+    u16_v = (e2e if args.target_format == "u16" else e2e_alt)["value"]
+    e2e["note"] += ("; like-for-like with the reference's fp32 hand-off: %.3g fits/s, with the sensor's uint16 "
+                    "hand-off (normalize_img moved onto the device): %.3g fits/s" % (f32_v, u16_v))
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, timed live with CUDA events ----
     peak, peak_src = measured_peaks()
     st = stage_times(step)
-    frag_key = "raster_fwd_kernel[fragments mode: +barycentrics]"
-    frag_ms = st.pop(frag_key)
-    dom = max(st, key=st.get)
-    dom_ms = st["raster_fwd_kernel"]
+    frag_ms = st.pop(FRAG_KEY)
+    fused_stages = {k: v for k, v in st.items() if not k.startswith("modular:")}
+    dom = max(fused_stages, key=fused_stages.get)
+    dom_ms = st[FUSED_KEY]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -357,35 +440,49 @@ def run_ours(args):
             traffic = tj.get("raster_fwd_kernel", {}).get(str(B))
         except Exception:
             traffic = None
-    achieved = RASTER_BYTES_PER_HAND * B / (dom_ms * 1e-3) / 1e9
-    step_gbs = BYTES_PER_FIT * B / (ms * 1e-3) / 1e9
+    achieved = RASTER_ALG_BYTES_PER_HAND * B / (dom_ms * 1e-3) / 1e9
+    step_gbs = BYTES_PER_FIT * G / (ms * 1e-3) / 1e9 / world
     roofline = {
-        "bound": "hbm", "kernel": "raster_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "raster_fwd_kernel<false> (forward + m2d loss + raster backward in one launch)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "bytes_per_launch": RASTER_BYTES_PER_HAND * B, "kernel_ms": dom_ms,
+        "bytes_per_launch": RASTER_ALG_BYTES_PER_HAND * B, "bytes_per_unit": RASTER_ALG_BYTES_PER_HAND,
+        "units_per_launch": B, "kernel_ms": dom_ms,
+        "bytes_moved_per_launch": RASTER_MOVED_BYTES_PER_HAND * B,
+        "achieved_moved": RASTER_MOVED_BYTES_PER_HAND * B / (dom_ms * 1e-3) / 1e9,
         "stage_ms": st, "slowest_stage": dom,
-        "step": {"bytes_per_fit": BYTES_PER_FIT, "achieved": step_gbs, "frac": step_gbs / peak},
+        "step": {"bytes_per_fit": BYTES_PER_FIT, "achieved": step_gbs, "frac": step_gbs / peak,
+                 "note": "per GPU: algorithmic bytes of the whole fit step x this GPU's fits/s over the measured HBM peak"},
     }
-    frag_bytes = (779 * 3 * 4 + 16 * 4 + 2 * CROP * 4 + 24 + 5 * CROP * CROP * 4) * B
+    frag_bytes = (779 * 3 * 4 + 20 * 4 + 2 * CROP * 4 + 24 + 5 * CROP * CROP * 4) * B
     roofline["fragments_mode"] = {
-        "what": "same kernel also writing barycentrics (3 x fp32 / pixel): depth + pix_to_face + bary out, mesh in; no loss fusion",
+        "what": "modular raster kernel also writing barycentrics (3 x fp32 / pixel): depth + pix_to_face + bary out, mesh in; no loss fusion",
         "kernel_ms": frag_ms, "bytes_per_launch": frag_bytes, "achieved": frag_bytes / (frag_ms * 1e-3) / 1e9,
         "frac": frag_bytes / (frag_ms * 1e-3) / 1e9 / peak}
     other = {}
     if world == 1 and not args.no_other_configs:
         for name, b2 in (("C1_batch128", 128), ("batch1024", 1024)):
-            s2 = FitStep(layer, b2, CROP, use_graph=not args.no_graph)
+            s2 = FitStep(layer, b2, CROP, use_graph=not args.no_graph, keep_pix_to_face=False)
             i2 = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(b2, seed=77).items()}
             s2.set_inputs(i2["params"], i2["center3d"], i2["cube"])
             s2.render_target(i2["params_target"])
             for _ in range(5):
                 s2.step()
             t2 = time_region(s2.step, 200)
+            t2_cold = timed_steps(s2.step, 30, L2Flusher(dev) if flush is None else flush)
             st2 = stage_times(s2, iters=50)
-            other[name] = {"hands": b2, "ms_per_step": t2, "fits_per_s": b2 / (t2 * 1e-3),
-                           "stage_ms": {k: round(v, 4) for k, v in st2.items()},
-                           "step_hbm_frac": BYTES_PER_FIT * b2 / (t2 * 1e-3) / 1e9 / peak,
-                           "note": "inputs fit in L2 at this size (no flush): latency/launch-bound regime"}
+            other[name] = {"hands": b2, "ms_per_step": t2_cold, "fits_per_s": b2 / (t2_cold * 1e-3),
+                           "ms_per_step_warm_l2": t2, "fits_per_s_warm_l2": b2 / (t2 * 1e-3),
+                           "launches_per_step": s2.launches_per_step,
+                           "stage_ms_warm_l2": {k: round(v, 4) for k, v in st2.items() if not k.startswith("modular:")},
+                           "step_hbm_frac": BYTES_PER_FIT * b2 / (t2_cold * 1e-3) / 1e9 / peak,
+                           "roofline": {"bound": "hbm", "kernel": "raster_fwd_kernel<false>",
+                                        "achieved": RASTER_ALG_BYTES_PER_HAND * b2 / (st2[FUSED_KEY] * 1e-3) / 1e9,
+                                        "peak": peak, "unit": "GB/s",
+                                        "frac": RASTER_ALG_BYTES_PER_HAND * b2 / (st2[FUSED_KEY] * 1e-3) / 1e9 / peak,
+                                        "note": "kernel timed back to back (inputs L2-resident at this size)"},
+                           "note": "ms_per_step: one event pair per step with an L2 flush in between (inputs would fit "
+                                   "L2); *_warm_l2: back-to-back graph replays"}
         # config C4 (BASELINE.json configs[4]): self-penetration + point-to-mesh terms, batch 1024
         from dsf_b200.mesh_loss import _PointFaceDistance
         b4, P = 1024, 2048
@@ -475,7 +572,7 @@ def run_ours(args):
             "note": "modular autograd path (image returned, loss as a separate kernel, torch ops for the view rotation)"}
         # the same configuration through the fused multi-view step (dsf_fit_step_views, CUDA-graph replay)
         from dsf_b200.fit import MultiViewFitStep
-        mv = MultiViewFitStep(layer, b3, V3, R3, use_graph=not args.no_graph)
+        mv = MultiViewFitStep(layer, b3, V3, R3, use_graph=not args.no_graph, keep_pix_to_face=False)
         mv.set_inputs(i3["params"], i3["center3d"], i3["cube"], rot3.reshape(b3, V3, 3), tgt3[:, 0])
         for _ in range(3):
             mv.step()
@@ -522,12 +619,13 @@ def run_ours(args):
                          f"oracle port of the reference CPU path, {dt:.1f} s"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-        "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph, "stream_chunks": args.chunks,
+        "launches_per_step": step.launches_per_step, "cuda_graph": not args.no_graph, "stream_chunks": step.chunks,
         "roofline": roofline, "cpu_baseline": cpu, "loss": float(step.totals[0]), "other_configs": other,
-        "e2e_%s_target" % alt_fmt: e2e_alt, "numa_bound": numa_bound,
+        "e2e_%s_target" % alt_fmt: e2e_alt, "numa_bound": numa_bound, "weak_scaling": weak,
+        "pix_to_face_plane": "not written: the rasteriser's epilogue emits the vertex gradient itself, nothing reads it",
     }
     print(json.dumps(line), flush=True)
 
@@ -538,11 +636,13 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="hands per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="global batch, sharded over the GPUs")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the weak-scaling companion measurement")
     ap.add_argument("--ref-batch", type=int, default=32, help="hands per CPU reference step (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--chunks", type=int, default=2, help="slices of the batch run on parallel streams")
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="slices of the shard run on parallel streams (0 = 2 from 2048 hands per GPU, else 1)")
     ap.add_argument("--target-format", choices=["u16", "f32"], default="u16",
                     help="how the target depth crop travels host->device in the e2e measurement")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin ranks to their GPU's NUMA node")

@@ -13,7 +13,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("DSF_B200_LIB", os.path.join(_HERE, "libdsf_b200.so"))   # override: kernel-tuning experiments
 
-VIEW_STRIDE = 16
+VIEW_STRIDE = 20
+RASTER_PERSPECTIVE_CORRECT = 1   # DSF_RASTER_PERSPECTIVE_CORRECT
+RASTER_SEPARATE_BACKWARD = 2     # DSF_RASTER_SEPARATE_BACKWARD
 NV, NVW, NJ, NJOUT, NSPHERE = 778, 779, 16, 21, 66
 
 c_float_p = C.POINTER(C.c_float)
@@ -60,9 +62,9 @@ SIGNATURES = {
     "dsf_mano_backward": (_I, [_VP, _I, C.POINTER(DsfManoParams), _F, _VP, _VP, _VP, _VP,
                                C.POINTER(DsfManoGrads), _VP, _VP]),
     "dsf_view_setup": (_I, [_I, _I, _VP, _VP, c_float_p, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "dsf_raster_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
+    "dsf_raster_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _I, _VP]),
     "dsf_raster_tiles": (_I, [_I]),
-    "dsf_raster_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "dsf_raster_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "dsf_depth_loss": (_I, [_I, _I, _I, _VP, _VP, _F, _F, _VP, _VP, _VP, _VP]),
     "dsf_coll_forward_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_point_face_forward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -73,15 +75,18 @@ SIGNATURES = {
     "dsf_joint_icp_backward": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_fit_workspace_floats": (_L, [_I, _I]),
     "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I, _VP, _I, _VP, c_float_p,
-                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dsf_raster_loss_workspace_floats": (_L, [_I, _I]),
+    "dsf_raster_loss_grad": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _F, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dsf_sum_totals": (_I, [_I, _VP, _I, _VP, _VP]),
     "dsf_fit_views_workspace_floats": (C.c_long, [_I, _I, _I]),
     "dsf_fit_step_views": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _VP,
-                                _VP, _VP, _VP, _VP]),
+                                _VP, _VP, _VP, _I, _VP]),
     "dsf_render_workspace_floats": (C.c_long, [_I]),
     "dsf_render_forward": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, c_float_p, _VP, _VP, _VP, _VP,
-                                _VP, _VP, _VP, _VP, _VP]),
+                                _VP, _VP, _VP, _VP, _I, _VP]),
     "dsf_render_backward": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, c_float_p, _VP, _VP, _VP, _VP,
-                                 _VP, _VP, _VP, _VP, _VP, _VP]),
+                                 _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dsf_crop_hand": (_I, [_I, _I, _VP, _VP, _I, _VP, _VP, _VP, c_float_p, _F, _F, _F, _VP, _VP, _VP]),
     "dsf_img2pcl": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, c_float_p, _F, _F, _I, C.c_ulonglong, _VP, _VP, _VP]),
     "dsf_target_from_u16": (_I, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP]),

@@ -56,6 +56,8 @@ struct DsfMano {
     int* faces;    // (n_faces,3)
     unsigned int* faces_packed;   // (n_faces) i0 | i1 << 10 | i2 << 20
     unsigned short* face_order;   // (n_faces) face ids, largest rest-pose area first
+    int* vf_ptr;                  // (780) CSR vertex -> incident face corners
+    unsigned short* vf_ent;       // (3 n_faces) face << 2 | corner
     int n_faces;
     float* coll_mask;  // (66,66)
     int parents[NJ];

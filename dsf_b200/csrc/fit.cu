@@ -2,36 +2,18 @@
 // -> MANO backward, as one fixed launch sequence on one stream (CUDA-graph capturable).
 // This is the chain Render.render (mano_layer.py:1071-1097) + train_render.py:728-732 + loss.backward()
 // runs through ~700 ATen/pytorch3d launches in the reference.
-#include "common.cuh"
+#include "raster.cuh"
 
-int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale, float* verts,
-                          float* joints, float* Rs, float* ws, cudaStream_t st);
-int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale,
-                           const float* verts, const float* joints, const float* g_verts,
-                           const float* g_joints, const DsfManoGrads* g, float* ws, cudaStream_t st);
-struct CropParams {
-    const float* joints;
-    const float* M;
-    int nj;
-    float fx, fy, px, py;
-    float off_xy, off_z, thick;
-};
-extern "C" int dsf_raster_tiles(int R);
-int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
-                            const float* place_off, const float* view, const float* xs, const float* ys,
-                            int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
-                            const float* target, float thr, float* parts_tile, const CropParams* crop,
-                            cudaStream_t st);
-int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
-                             const float* place_off, const float* view, const float* xs, const float* ys,
-                             int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
-                             const float* img, const float* parts, float gscale, float thr, const CropParams* crop,
-                             cudaStream_t st);
-int dsf_fold_loss_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
-                       cudaStream_t st);
+#define AUX_THREADS_RED 256
+
+// workspace of one fused step (floats): MANO scratch | per-tile loss sums | per-tile gradient flags |
+// per-tile vertex-gradient shares (the first NVW*3 floats per hand double as g_verts of the unfused path) |
+// the rasteriser's done-counter
+static inline size_t fit_ws_parts(int n_mesh_mano) { return (size_t)n_mesh_mano * WS_PER_HAND; }
 
 extern "C" long dsf_fit_workspace_floats(int batch, int R) {
-    return (long)batch * (WS_PER_HAND + 2L * dsf_raster_tiles(R) + NVW * 3);
+    const long nt = dsf_raster_tiles(R);
+    return (long)batch * (WS_PER_HAND + 2L * nt + nt + nt * NVW * 3) + 4;
 }
 
 extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
@@ -40,17 +22,22 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
                             int n_crop_joints,
                             const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                             float* verts, float* joints, float* g_params, float* parts, float* totals,
-                            float* workspace, dsfStream_t stream) {
+                            float* workspace, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && target, "null input");
-    DSF_REQUIRE(img && pix_to_face && verts && joints && g_params && parts && totals && workspace, "null output");
+    DSF_REQUIRE(img && verts && joints && g_params && parts && totals && workspace, "null output");
     DSF_REQUIRE(batch > 0 && batch <= 65535, "batch must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
+    const bool fused = dsf_raster_fused_grad_ok(h, flags);
+    DSF_REQUIRE(fused || pix_to_face, "pix_to_face may only be NULL when the rasteriser produces the gradient itself "
+                                      "(no perspective correction)");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws_mano = workspace;
     const int n_tiles = dsf_raster_tiles(R);
-    float* parts_tile = workspace + (size_t)batch * WS_PER_HAND;
-    float* g_verts = parts_tile + (size_t)batch * n_tiles * 2;
+    float* parts_tile = workspace + fit_ws_parts(batch);
+    int* gv_flag = reinterpret_cast<int*>(parts_tile + (size_t)batch * n_tiles * 2);
+    float* gv_tile = reinterpret_cast<float*>(gv_flag + (size_t)batch * n_tiles);
+    float* g_verts = gv_tile;
     const float thr = 0.99f;
     DSF_REQUIRE(!crop_joints || (crop_M && intr4 && n_crop_joints > 0), "crop_joints needs crop_M, intr4 and a joint count");
     // crop_hand defaults of data/render_loader.py:1209 (offsetxy=25, offsetz=20, hand_thickness=20)
@@ -70,22 +57,82 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     g.beta = g_params + 48; g.ld_beta = 62;
     g.cam = g_params + 58; g.ld_cam = 62;
     const float unit_scale = 1000.f * (1.f / 125.f);   // get_mano_vertices(..., global_scale=1/125), :1077
+    const float gscale = loss_weight / (float)(norm_batch > 0 ? norm_batch : batch);
 
     int rc = dsf_mano_forward_impl(h, batch, &p, unit_scale, verts, joints, nullptr, ws_mano, st);
     if (rc) return rc;
-    // rasterise + normalise; the m2d loss partial sums fall out of the epilogue (no extra pass)
+    // rasterise + normalise; the per-tile m2d loss sums and - without perspective correction - the vertex
+    // gradient itself fall out of the epilogue.  The loss records ride along with the MANO backward kernels
+    // (parts by the skinning backward, totals by block 0 of the pose backward): no fold / totals launches.
+    RasterFused rf = {fused ? gv_tile : nullptr, gv_flag};
     rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr,
-                                 nullptr, nullptr, target, thr, parts_tile, cropp, st);
+                                 nullptr, nullptr, target, thr, parts_tile, cropp, flags, &rf, st);
     if (rc) return rc;
-    rc = dsf_fold_loss_impl(batch, n_tiles, loss_weight, parts_tile, parts, totals, st);
-    if (rc) return rc;
-    // backward recomputes d loss / d img per pixel from (target, img, N_b): no gradient image in HBM
+    LossFold lf = {parts_tile, n_tiles, batch, parts, totals, loss_weight};
+    if (fused) {
+        GradTiles gt = {gv_tile, gv_flag, parts_tile, n_tiles, gscale};
+        return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, nullptr, nullptr, &g, ws_mano, &gt,
+                                      cube, &lf, st);
+    }
+    // perspective-correct depth is not affine in the sample position: separate backward kernel, which
+    // recomputes d loss / d img per pixel from (target, img, N_b) - no gradient image in HBM
     rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, nullptr,
-                                  g_verts, target, img, parts, loss_weight / (float)(norm_batch > 0 ? norm_batch : batch), thr,
-                                  cropp, st);
+                                  g_verts, target, img, parts_tile, gscale, thr, cropp, flags, st);
     if (rc) return rc;
-    rc = dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
-    return rc;
+    return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, nullptr,
+                                  nullptr, &lf, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The rasteriser's fused launch on its own (R1 + R4 + L2 + R2 for camera-space vertices from any source):
+// rasterise, normalise, m2d loss against the target and the per-tile shares of d loss / d verts_cam, then
+// one small kernel that sums the shares and applies each mesh's loss normalisation.
+// ------------------------------------------------------------------------------------------------
+extern "C" long dsf_raster_loss_workspace_floats(int n_mesh, int R) {
+    const long nt = dsf_raster_tiles(R);
+    return (long)n_mesh * (2L * nt + nt + nt * NVW * 3) + 4;
+}
+
+__global__ void __launch_bounds__(AUX_THREADS_RED)
+grad_tiles_reduce_kernel(GradTiles gt, const float* __restrict__ view, float* __restrict__ g_verts) {
+    const int mesh = blockIdx.x;
+    __shared__ float s_scale;
+    if (threadIdx.x == 0) s_scale = grad_tiles_scale(gt, mesh, view[(size_t)mesh * VIEW + 5]);
+    __syncthreads();
+    const float sc = s_scale;
+    for (int i = threadIdx.x; i < NVW * 3; i += AUX_THREADS_RED)
+        g_verts[(size_t)mesh * NVW * 3 + i] = sc * grad_tiles_load(gt, mesh, i);
+}
+
+extern "C" int dsf_raster_loss_grad(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
+                                    const float* xs, const float* ys, int R, const float* target, float thr,
+                                    float loss_weight, int norm_batch, float* img, int* pix_to_face, float* parts,
+                                    float* totals, float* g_verts_cam, float* workspace, int flags,
+                                    dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(h && verts_cam && view && xs && ys && target && img && parts && totals && workspace, "null argument");
+    DSF_REQUIRE(n_mesh > 0 && n_mesh <= 65535, "n_mesh must be in [1,65535] per call");
+    DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
+    DSF_REQUIRE(dsf_raster_fused_grad_ok(h, flags & 3), "fused loss gradient needs flags without PERSPECTIVE_CORRECT "
+                                                    "(use dsf_raster_forward + dsf_depth_loss + dsf_raster_backward)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = dsf_raster_tiles(R);
+    float* parts_tile = workspace;
+    int* gv_flag = reinterpret_cast<int*>(parts_tile + (size_t)n_mesh * n_tiles * 2);
+    float* gv_tile = reinterpret_cast<float*>(gv_flag + (size_t)n_mesh * n_tiles);
+    RasterFused rf = {gv_tile, gv_flag};
+    if (flags & 256) rf.gv_tile = nullptr;          // tuning aid: forward + loss sums only
+    int rc = dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face, nullptr,
+                                     nullptr, nullptr, target, thr, parts_tile, nullptr, flags & 3, &rf, st);
+    if (rc) return rc;
+    rc = dsf_fold_totals_impl(n_mesh, n_tiles, loss_weight, parts_tile, parts, totals, st);
+    if (rc) return rc;
+    if (g_verts_cam) {
+        GradTiles gt = {gv_tile, gv_flag, parts_tile, n_tiles, loss_weight / (float)(norm_batch > 0 ? norm_batch : n_mesh)};
+        grad_tiles_reduce_kernel<<<n_mesh, AUX_THREADS_RED, 0, st>>>(gt, view, g_verts_cam);
+        DSF_CHECK_LAUNCH();
+    }
+    return DSF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -189,7 +236,7 @@ extern "C" int dsf_render_forward(const DsfMano* h, int batch, int R, const floa
                                   const float* center3d, const float* cube, const float* view, const float* xs,
                                   const float* ys, const float* M, const float* intr4, float* img, int* pix_to_face,
                                   float* verts, float* joints, float* joint_uvd, float* joint_xyz, float* mesh_xyz,
-                                  float* workspace, dsfStream_t stream) {
+                                  float* workspace, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && M && intr4, "null input");
     DSF_REQUIRE(img && pix_to_face && verts && joints && workspace, "null output");
@@ -202,7 +249,7 @@ extern "C" int dsf_render_forward(const DsfMano* h, int batch, int R, const floa
     int rc = dsf_mano_forward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, nullptr, workspace, st);
     if (rc) return rc;
     rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr, nullptr,
-                                 nullptr, nullptr, 0.99f, nullptr, nullptr, st);
+                                 nullptr, nullptr, 0.99f, nullptr, nullptr, flags, nullptr, st);
     if (rc) return rc;
     if (joint_uvd || joint_xyz || mesh_xyz) {
         render_aux_kernel<<<batch, AUX_THREADS, 0, st>>>(verts, joints, center3d, cube, M, intr4[0], intr4[1], intr4[2],
@@ -217,7 +264,7 @@ extern "C" int dsf_render_backward(const DsfMano* h, int batch, int R, const flo
                                    const float* ys, const float* M, const float* intr4, const float* verts,
                                    const float* joints, const int* pix_to_face, const float* g_img,
                                    const float* g_joint_uvd, const float* g_joint_xyz, const float* g_mesh_xyz,
-                                   float* g_params, float* workspace, dsfStream_t stream) {
+                                   float* g_params, float* workspace, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && M && intr4 && verts && joints && pix_to_face,
                 "null input");
@@ -233,14 +280,15 @@ extern "C" int dsf_render_backward(const DsfMano* h, int batch, int R, const flo
     int rc;
     if (g_img) {
         rc = dsf_raster_backward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, pix_to_face, g_img, g_verts,
-                                      nullptr, nullptr, nullptr, 0.f, 0.99f, nullptr, st);
+                                      nullptr, nullptr, nullptr, 0.f, 0.99f, nullptr, flags, st);
         if (rc) return rc;
     }
     render_aux_bwd_kernel<<<batch, AUX_THREADS, 0, st>>>(joints, center3d, cube, M, intr4[0], intr4[1], (float)R,
                                                          g_joint_uvd, g_joint_xyz, g_mesh_xyz, g_img ? 1 : 0, g_verts,
                                                          g_joints);
     DSF_CHECK_LAUNCH();
-    return dsf_mano_backward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, g_verts, g_joints, &g, workspace, st);
+    return dsf_mano_backward_impl(h, batch, &p, 1000.f * (1.f / 125.f), verts, joints, g_verts, g_joints, &g, workspace,
+                                  nullptr, nullptr, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,20 +317,34 @@ views_place_kernel(int views, const float* __restrict__ verts, const float* __re
     }
 }
 
-// g_verts[b] = sum_v R[b, v]^T g_cam[b, v] * cube[b] / 2
+// g_verts[b] = sum_v R[b, v]^T g_cam[b, v] * cube[b] / 2; g_cam either dense (B*V,779,3) or the rasteriser's
+// per-tile shares (gt.gv_tile != null: sum the flagged tiles, times the mesh's loss normalisation)
 __global__ void __launch_bounds__(AUX_THREADS)
-views_place_bwd_kernel(int views, const float* __restrict__ g_cam, const float* __restrict__ cube,
+views_place_bwd_kernel(int views, const float* __restrict__ g_cam, GradTiles gt, const float* __restrict__ cube,
                        const float* __restrict__ rot, float* __restrict__ g_verts) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const float hx = cube[3 * b] * 0.5f, hy = cube[3 * b + 1] * 0.5f, hz = cube[3 * b + 2] * 0.5f;
+    __shared__ float s_scale[32];
+    if (gt.gv_tile && tid < views && tid < 32) s_scale[tid] = grad_tiles_scale(gt, b * views + tid, hz);
+    __syncthreads();
     for (int i = tid; i < NVW; i += AUX_THREADS) {
         float ax = 0.f, ay = 0.f, az = 0.f;
         for (int v = 0; v < views; ++v) {                       // fixed order: deterministic sum
             const float* R = rot + ((size_t)b * views + v) * 9;
-            const float* g = g_cam + (((size_t)b * views + v) * NVW + i) * 3;
-            ax += R[0] * g[0] + R[3] * g[1] + R[6] * g[2];
-            ay += R[1] * g[0] + R[4] * g[1] + R[7] * g[2];
-            az += R[2] * g[0] + R[5] * g[1] + R[8] * g[2];
+            float g0, g1, g2;
+            if (gt.gv_tile) {
+                const int mesh = b * views + v;
+                const float sc = s_scale[v];
+                g0 = sc * grad_tiles_load(gt, mesh, 3 * i);
+                g1 = sc * grad_tiles_load(gt, mesh, 3 * i + 1);
+                g2 = sc * grad_tiles_load(gt, mesh, 3 * i + 2);
+            } else {
+                const float* g = g_cam + (((size_t)b * views + v) * NVW + i) * 3;
+                g0 = g[0]; g1 = g[1]; g2 = g[2];
+            }
+            ax += R[0] * g0 + R[3] * g1 + R[6] * g2;
+            ay += R[1] * g0 + R[4] * g1 + R[7] * g2;
+            az += R[2] * g0 + R[5] * g1 + R[8] * g2;
         }
         float* o = g_verts + ((size_t)b * NVW + i) * 3;
         o[0] = ax * hx; o[1] = ay * hy; o[2] = az * hz;
@@ -290,27 +352,33 @@ views_place_bwd_kernel(int views, const float* __restrict__ g_cam, const float* 
 }
 
 extern "C" long dsf_fit_views_workspace_floats(int batch, int views, int R) {
-    const long nm = (long)batch * views;
-    return (long)batch * (WS_PER_HAND + NVW * 3) + nm * (2L * NVW * 3 + 2L * dsf_raster_tiles(R));
+    const long nm = (long)batch * views, nt = dsf_raster_tiles(R);
+    const long grad = nt * NVW * 3 > NVW * 3 ? nt * NVW * 3 : NVW * 3;
+    return (long)batch * (WS_PER_HAND + NVW * 3) + nm * ((long)NVW * 3 + grad + 3L * nt) + 4;
 }
 
 extern "C" int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R, const float* params,
                                   const float* center3d, const float* cube, const float* rot, const float* view,
                                   const float* xs, const float* ys, const float* target, float loss_weight,
                                   float* img, int* pix_to_face, float* verts, float* joints, float* g_params,
-                                  float* parts, float* totals, float* workspace, dsfStream_t stream) {
+                                  float* parts, float* totals, float* workspace, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && params && center3d && cube && rot && view && xs && ys && target, "null input");
-    DSF_REQUIRE(img && pix_to_face && verts && joints && g_params && parts && totals && workspace, "null output");
-    DSF_REQUIRE(batch > 0 && views > 0 && (long)batch * views <= 65535, "batch * views must be in [1,65535] per call");
+    DSF_REQUIRE(img && verts && joints && g_params && parts && totals && workspace, "null output");
+    DSF_REQUIRE(batch > 0 && views > 0 && views <= 32 && (long)batch * views <= 65535,
+                "views must be in [1,32], batch * views in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
+    const bool fused = dsf_raster_fused_grad_ok(h, flags);
+    DSF_REQUIRE(fused || pix_to_face, "pix_to_face may only be NULL without perspective correction");
     cudaStream_t st = (cudaStream_t)stream;
     const int nm = batch * views, n_tiles = dsf_raster_tiles(R);
+    const size_t grad = (size_t)(n_tiles > 1 ? n_tiles : 1) * NVW * 3;
     float* ws_mano = workspace;
     float* g_verts = workspace + (size_t)batch * WS_PER_HAND;
     float* verts_cam = g_verts + (size_t)batch * NVW * 3;
-    float* g_cam = verts_cam + (size_t)nm * NVW * 3;
-    float* parts_tile = g_cam + (size_t)nm * NVW * 3;
+    float* g_cam = verts_cam + (size_t)nm * NVW * 3;              // dense cotangent, or the per-tile shares
+    float* parts_tile = g_cam + (size_t)nm * grad;
+    int* gv_flag = reinterpret_cast<int*>(parts_tile + (size_t)nm * n_tiles * 2);
     const float thr = 0.99f;
     DsfManoParams p;
     DsfManoGrads g;
@@ -320,15 +388,21 @@ extern "C" int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R,
     if (rc) return rc;
     views_place_kernel<<<batch, AUX_THREADS, 0, st>>>(views, verts, center3d, cube, rot, verts_cam);
     DSF_CHECK_LAUNCH();
+    RasterFused rf = {fused ? g_cam : nullptr, gv_flag};
     rc = dsf_raster_forward_impl(h, nm, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face, nullptr, nullptr,
-                                 nullptr, target, thr, parts_tile, nullptr, st);
+                                 nullptr, target, thr, parts_tile, nullptr, flags, &rf, st);
     if (rc) return rc;
-    rc = dsf_fold_loss_impl(nm, n_tiles, loss_weight, parts_tile, parts, totals, st);
-    if (rc) return rc;
-    rc = dsf_raster_backward_impl(h, nm, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face, nullptr, g_cam, target,
-                                  img, parts, loss_weight / (float)nm, thr, nullptr, st);
-    if (rc) return rc;
-    views_place_bwd_kernel<<<batch, AUX_THREADS, 0, st>>>(views, g_cam, cube, rot, g_verts);
+    GradTiles gt = {};
+    if (fused) {
+        gt = GradTiles{g_cam, gv_flag, parts_tile, n_tiles, loss_weight / (float)nm};
+    } else {
+        rc = dsf_raster_backward_impl(h, nm, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face, nullptr, g_cam,
+                                      target, img, parts_tile, loss_weight / (float)nm, thr, nullptr, flags, st);
+        if (rc) return rc;
+    }
+    views_place_bwd_kernel<<<batch, AUX_THREADS, 0, st>>>(views, g_cam, gt, cube, rot, g_verts);
     DSF_CHECK_LAUNCH();
-    return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, st);
+    LossFold lf = {parts_tile, n_tiles, nm, parts, totals, loss_weight};     // parts per mesh + totals: pose backward, block 0
+    return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, nullptr,
+                                  nullptr, &lf, st);
 }

@@ -8,7 +8,7 @@
 #include <utility>
 #include <vector>
 
-#include "common.cuh"
+#include "raster.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error / launch bookkeeping
@@ -196,6 +196,18 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
         for (int f = 0; f < host->n_faces; ++f) order[f] = (unsigned short)area[f].second;
         rc |= upload(&h->face_order, order.data(), order.size());
     }
+    {   // vertex -> incident face corners (the rasteriser's gradient gather)
+        std::vector<int> vptr(NVW + 1, 0);
+        for (int i = 0; i < host->n_faces * 3; ++i) vptr[host->faces[i] + 1]++;
+        for (int v = 0; v < NVW; ++v) vptr[v + 1] += vptr[v];
+        std::vector<unsigned short> vent((size_t)host->n_faces * 3 + 1, 0);
+        std::vector<int> fill(vptr.begin(), vptr.end() - 1);
+        if (host->n_faces * 4 < 65536)
+            for (int f = 0; f < host->n_faces; ++f)
+                for (int c = 0; c < 3; ++c) vent[fill[host->faces[3 * f + c]]++] = (unsigned short)(f * 4 + c);
+        rc |= upload(&h->vf_ptr, vptr.data(), vptr.size());
+        rc |= upload(&h->vf_ent, vent.data(), vent.size());
+    }
     rc |= upload(&h->coll_mask, mask.data(), mask.size());
     h->n_faces = host->n_faces;
     if (rc) {
@@ -210,7 +222,7 @@ extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
     void* ptrs[] = {h->BTh, h->BTl, h->Bh, h->Bl, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
                     h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx, h->wj_w, h->faces, h->faces_packed,
-                    h->face_order, h->coll_mask};
+                    h->face_order, h->coll_mask, h->vf_ptr, h->vf_ent};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free(h);
@@ -468,7 +480,8 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
                      const float* __restrict__ cam, int ld_cam,
                      float unit_scale, const float* __restrict__ verts, const float* __restrict__ joints,
                      const float* __restrict__ g_verts, const float* __restrict__ g_joints,
-                     float* __restrict__ g_cam, int ld_gcam) {
+                     float* __restrict__ g_cam, int ld_gcam, GradTiles gt, const float* __restrict__ cube,
+                     LossFold lf) {
     __shared__ float sg[NVW * 3];
     __shared__ float svp[NV * 3];
     __shared__ float sGr[NJ][9];
@@ -490,8 +503,24 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
     float pt[4] = {0.f, 0.f, 0.f, 0.f};
     const float* gv = g_verts ? g_verts + (size_t)hand * NVW * 3 : nullptr;
     const float* vo = verts + (size_t)hand * NVW * 3;
+    // vertex cotangent straight from the rasteriser's per-tile shares (fused step): sum the tiles, apply the
+    // hand's loss normalisation gk / zhalf
+    const float gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
+    if (lf.parts && lf.n_mesh == B && tid == 0) {            // per-hand loss record = sum of its tiles
+        float a = 0.f, c = 0.f;
+        for (int t = 0; t < lf.n_tiles; ++t) {
+            a += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2];
+            c += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2 + 1];
+        }
+        lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
+    }
     for (int v = tid; v < NVW; v += SKB_T) {
         float a = gv ? gv[3 * v] : 0.f, b = gv ? gv[3 * v + 1] : 0.f, c = gv ? gv[3 * v + 2] : 0.f;
+        if (gt.gv_tile) {
+            a = gts * grad_tiles_load(gt, hand, 3 * v);
+            b = gts * grad_tiles_load(gt, hand, 3 * v + 1);
+            c = gts * grad_tiles_load(gt, hand, 3 * v + 2);
+        }
         sg[3 * v] = a; sg[3 * v + 1] = b; sg[3 * v + 2] = c;
         pt[1] += a; pt[2] += b; pt[3] += c;
         pt[0] += a * (vo[3 * v] - tx) + b * (vo[3 * v + 1] - ty) + c * (vo[3 * v + 2] - tz);
@@ -611,7 +640,8 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(POSE_HPB* NJ)
 mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __restrict__ comp,
-                     const float* __restrict__ JS, ChainTopo topo, const float* __restrict__ ws, int n_split) {
+                     const float* __restrict__ JS, ChainTopo topo, const float* __restrict__ ws, int n_split,
+                     LossFold lf) {
     __shared__ float s_acc[POSE_HPB][NJ][15];   // gGr[9] gGt[3] gJ[3]
     __shared__ float s_gang[POSE_HPB][48];
     const int hl = threadIdx.x / NJ;
@@ -725,6 +755,31 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
             g.beta[(size_t)hh * g.ld_beta + j] = a;
         }
     }
+    // loss totals of the step (last kernel of the chain): block 0 reduces the per-tile sums in a fixed order
+    if (lf.totals && blockIdx.x == 0) {
+        __shared__ float s_red[POSE_HPB * NJ / 32][3];
+        float sum = 0.f, cnt = 0.f, per = 0.f;
+        for (int b = threadIdx.x; b < lf.n_mesh; b += POSE_HPB * NJ) {
+            float a = 0.f, c = 0.f;
+            for (int t = 0; t < lf.n_tiles; ++t) {
+                a += lf.parts_tile[((size_t)b * lf.n_tiles + t) * 2];
+                c += lf.parts_tile[((size_t)b * lf.n_tiles + t) * 2 + 1];
+            }
+            if (lf.n_mesh != B) { lf.parts[2 * b] = a; lf.parts[2 * b + 1] = c; }     // multi-view: parts per mesh
+            sum += a; cnt += c; per += a / (c + 1e-8f);
+        }
+        sum = warp_sum(sum); cnt = warp_sum(cnt); per = warp_sum(per);
+        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = sum; s_red[threadIdx.x >> 5][1] = cnt; s_red[threadIdx.x >> 5][2] = per; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            for (int w = 0; w < POSE_HPB * NJ / 32; ++w) { a += s_red[w][0]; b += s_red[w][1]; c += s_red[w][2]; }
+            lf.totals[0] = lf.weight * c / (float)lf.n_mesh;
+            lf.totals[1] = a;
+            lf.totals[2] = b;
+            lf.totals[3] = lf.weight * c;      // un-normalised, for summing over slices / ranks
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -756,20 +811,23 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
 
 int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale,
                            const float* verts, const float* joints, const float* g_verts,
-                           const float* g_joints, const DsfManoGrads* g, float* ws, cudaStream_t st) {
+                           const float* g_joints, const DsfManoGrads* g, float* ws, const GradTiles* gt,
+                           const float* cube, const LossFold* lf, cudaStream_t st) {
     int rc = ensure_constants();
     if (rc) return rc;
     ChainTopo topo = topo_of(h);
     mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx,
                                               h->wj_w, p->cam, p->ld_cam,
                                               unit_scale, verts, joints, g_verts, g_joints,
-                                              p->cam ? g->cam : nullptr, g->ld_cam);
+                                              p->cam ? g->cam : nullptr, g->ld_cam, gt ? *gt : GradTiles{}, cube,
+                                              lf ? *lf : LossFold{});
     DSF_CHECK_LAUNCH();
     // g_X = g_vposed . basis^T as BLEND_SPLITS split-K partials (summed by the pose backward kernel)
     rc = dsf_blend_backward_gemm(B, ws + WS_GVP, WS_PER_HAND, h->Bh, h->Bl, ws + WS_GX, WS_PER_HAND, KP, st);
     if (rc) return rc;
     mano_pose_bwd_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, *g, h->comp, h->JS,
-                                                                                  topo, ws, dsf_blend_backward_splits(B));
+                                                                                  topo, ws, dsf_blend_backward_splits(B),
+                                                                                  lf ? *lf : LossFold{});
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
@@ -797,5 +855,5 @@ extern "C" int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParam
     int rc = check_params(p);
     if (rc) return rc;
     return dsf_mano_backward_impl(h, batch, p, unit_scale, verts, joints, g_verts, g_joints, g, workspace,
-                                  (cudaStream_t)stream);
+                                  nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }

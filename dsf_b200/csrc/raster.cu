@@ -11,7 +11,7 @@
 // agree bit for bit on identical inputs.
 #include <math.h>
 
-#include "common.cuh"
+#include "raster.cuh"
 
 #define EPS 1e-8f
 
@@ -84,6 +84,8 @@ __global__ void view_setup_kernel(int mode, int B, const float* __restrict__ cen
         vw[5] = zh;
         vw[6] = __fdiv_rn(__fsub_rn(__fadd_rn(cz, zh), cz), zh);   // background after normalize_img
         vw[15] = 0.f;
+        vw[16] = (float)(mode == 0 ? R : (W > H ? W : H));   // side of the raster the samples index into
+        vw[17] = 0.f; vw[18] = 0.f; vw[19] = 0.f;
         if (mode == 0) {
             float half = (float)R * 0.5f;
             float fxc = __fmul_rn(sM[0], fx), fyc = __fmul_rn(sM[2], fy);
@@ -166,6 +168,7 @@ struct ViewRec {
     float fxn, fyn, pxn, pyn, zc, zh, bg, ax, bx, ay, by;
     int xlo, xhi, ylo, yhi;
     bool affine;
+    float S;
 };
 
 __device__ __forceinline__ ViewRec load_view(const float* v) {
@@ -174,6 +177,7 @@ __device__ __forceinline__ ViewRec load_view(const float* v) {
     r.ax = v[7]; r.bx = v[8]; r.ay = v[9]; r.by = v[10];
     r.xlo = (int)v[11]; r.xhi = (int)v[12]; r.ylo = (int)v[13]; r.yhi = (int)v[14];
     r.affine = v[15] != 0.f;
+    r.S = v[16];
     return r;
 }
 
@@ -215,26 +219,63 @@ struct FragEval {
     bool ok;
 };
 
-// full oracle-order evaluation of one (pixel, face) pair
-__device__ __forceinline__ FragEval eval_fragment(float px, float py, float x0, float y0, float z0, float x1,
-                                                  float y1, float z1, float x2, float y2, float z2, float area) {
+// full oracle-order evaluation of one (pixel, face) pair.  PERSP = pytorch3d's perspective_correct:
+// false (the 0.4.0 RasterizationSettings default the reference runs with, mano_layer.py:946-950 passes no
+// such argument) interpolates z with the screen-space barycentrics, true applies
+// BarycentricPerspectiveCorrection first.
+template <bool PERSP>
+__device__ __forceinline__ FragEval eval_fragment_e(float e0, float e1, float e2, float z0, float z1, float z2,
+                                                    float area) {
     FragEval r;
-    float e0 = edge_rn(px, py, x1, y1, x2, y2);
-    float e1 = edge_rn(px, py, x2, y2, x0, y0);
-    float e2 = edge_rn(px, py, x0, y0, x1, y1);
     r.w0 = __fdiv_rn(e0, area);
     r.w1 = __fdiv_rn(e1, area);
     r.w2 = __fdiv_rn(e2, area);
-    float t0 = __fmul_rn(__fmul_rn(r.w0, z1), z2);
-    float t1 = __fmul_rn(__fmul_rn(z0, r.w1), z2);
-    float t2 = __fmul_rn(__fmul_rn(z0, z1), r.w2);
-    float den = __fadd_rn(__fadd_rn(t0, t1), t2);
-    r.b0 = __fdiv_rn(t0, den);
-    r.b1 = __fdiv_rn(t1, den);
-    r.b2 = __fdiv_rn(t2, den);
+    if (PERSP) {
+        float t0 = __fmul_rn(__fmul_rn(r.w0, z1), z2);
+        float t1 = __fmul_rn(__fmul_rn(z0, r.w1), z2);
+        float t2 = __fmul_rn(__fmul_rn(z0, z1), r.w2);
+        float den = __fadd_rn(__fadd_rn(t0, t1), t2);
+        r.b0 = __fdiv_rn(t0, den);
+        r.b1 = __fdiv_rn(t1, den);
+        r.b2 = __fdiv_rn(t2, den);
+    } else {
+        r.b0 = r.w0; r.b1 = r.w1; r.b2 = r.w2;
+    }
     r.pz = __fadd_rn(__fadd_rn(__fmul_rn(r.b0, z0), __fmul_rn(r.b1, z1)), __fmul_rn(r.b2, z2));
     r.ok = !(r.pz < 0.f) && r.b0 > 0.f && r.b1 > 0.f && r.b2 > 0.f;
     return r;
+}
+
+template <bool PERSP>
+__device__ __forceinline__ FragEval eval_fragment(float px, float py, float x0, float y0, float z0, float x1,
+                                                  float y1, float z1, float x2, float y2, float z2, float area) {
+    return eval_fragment_e<PERSP>(edge_rn(px, py, x1, y1, x2, y2), edge_rn(px, py, x2, y2, x0, y0),
+                                  edge_rn(px, py, x0, y0, x1, y1), z0, z1, z2, area);
+}
+
+// Gradient of L = sum_p g(p) pz(p) over the pixels p of ONE face when depth is interpolated with the
+// screen-space barycentrics (no perspective correction): pz(p) = [z0 e0 + z1 e1 + z2 e2] / (A + eps) is affine
+// in p, so L depends on the pixels only through S0 = sum g and U = sum g (p - v0):
+//   L = k (z0 A S0 + dz1 E1 + dz2 E2),  k = 1 / (A + eps),  A = b x a (the oracle's area without eps),
+//   a = v1 - v0, b = v2 - v0, dz_i = z_i - z0, E1 = Uy bx - Ux by = sum g e1(p), E2 = Ux ay - Uy ax = sum g e2(p).
+// The form is chosen for conditioning: the per-pixel chain rule of the reference (g_w_i = g z_i, then through
+// w_i = e_i / area) subtracts two O(z S0) terms that agree to ~1e-4 of their size; here
+// d L / d A = k^2 (z0 S0 eps - D) (using 1 - A k = eps k) and they never meet.  Verified against float64 autograd.
+// out: g[0..2] = d L / d (x0, y0, z0), g[3..5] vertex 1, g[6..8] vertex 2.
+template <typename T>
+__device__ __forceinline__ void face_grad(T z0, T ax, T ay, T dz1, T bx, T by, T dz2, T S0, T Ux, T Uy, T* g) {
+    const T A = bx * ay - by * ax;
+    const T k = T(1) / (A + T(1e-8));
+    const T E1 = Uy * bx - Ux * by, E2 = Ux * ay - Uy * ax;
+    const T gA = k * k * (z0 * S0 * T(1e-8) - (dz1 * E1 + dz2 * E2));
+    const T g_ax = -gA * by - k * dz2 * Uy, g_ay = gA * bx + k * dz2 * Ux;
+    const T g_bx = gA * ay + k * dz1 * Uy, g_by = -gA * ax - k * dz1 * Ux;
+    const T g_Ux = k * (dz2 * ay - dz1 * by), g_Uy = k * (dz1 * bx - dz2 * ax);
+    g[3] = g_ax; g[4] = g_ay; g[5] = k * E1;
+    g[6] = g_bx; g[7] = g_by; g[8] = k * E2;
+    g[0] = -g_ax - g_bx - S0 * g_Ux;
+    g[1] = -g_ay - g_by - S0 * g_Uy;
+    g[2] = k * A * S0 - g[5] - g[8];
 }
 
 __device__ __forceinline__ float seg_dist_rn(float px, float py, float ax, float ay, float bx, float by) {
@@ -256,14 +297,6 @@ __device__ __forceinline__ float seg_dist_rn(float px, float py, float ax, float
 // around the teacher skeleton - data/render_loader.py:1209-1227 with uvdImg2xyzImg (:1190-1200),
 // uvd_nl2xyz_tensor (:1044-1057) and pointsImgTo3D (:336-343, flip = 1).
 // ------------------------------------------------------------------------------------------------
-struct CropParams {
-    const float* joints;   // (B, nj, 3) normalised teacher joints, or nullptr = no crop
-    const float* M;        // (B,3,3) axis-aligned crop transform
-    int nj;
-    float fx, fy, px, py;
-    float off_xy, off_z, thick;
-};
-
 struct CropBox {
     float lo[3], hi[3];
     float s_x, t_x, s_y, t_y;
@@ -388,21 +421,45 @@ static size_t raster_fwd_smem(int R, int F) {
 }
 
 // exact evaluation of pixel (i,j) against face f, commit to the z-buffer
+template <bool PERSP>
 __device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned int f, int i, int j, int tx0,
-                                                int ty0) {
+                                                int ty0, bool zmin_bounds) {
     const unsigned int pk = s.fp[f];
     const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
     const float z0 = s.vn[3 * a0 + 2], z1 = s.vn[3 * a1 + 2], z2 = s.vn[3 * a2 + 2];
     unsigned long long* slot = &s.key[(j - ty0) * RT_TW + (i - tx0)];
-    // early z: pz is a convex combination of (z0,z1,z2) up to a few ulp, so a face whose nearest
-    // vertex is clearly behind the stored depth cannot win (NaN compare = empty pixel = proceed)
+    // early z: with perspective correction pz is a convex combination of (z0,z1,z2) up to a few ulp; without
+    // it the weights sum to A / (A + eps), i.e. pz >= zmin (1 - eps / A) for a front-facing face (more for a
+    // back-facing one).  zmin_bounds says eps / A is below the 1e-4 margin (phase A knows the area), so a face
+    // whose nearest vertex is clearly behind the stored depth cannot win (NaN compare = empty pixel = proceed).
     const float cur = __uint_as_float((unsigned int)(*slot >> 32));
-    if (fminf(z0, fminf(z1, z2)) * 0.99999f > cur) return;
+    if (zmin_bounds && fminf(z0, fminf(z1, z2)) * 0.9999f > cur) return;
     const float x0 = s.vn[3 * a0], y0 = s.vn[3 * a0 + 1];
     const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
     const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
+    const float px = s.xs[i], py = s.ys[j];
     const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
-    FragEval fe = eval_fragment(s.xs[i], s.ys[j], x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
+    const float e0 = edge_rn(px, py, x1, y1, x2, y2);
+    const float e1 = edge_rn(px, py, x2, y2, x0, y0);
+    const float e2 = edge_rn(px, py, x0, y0, x1, y1);
+    // Sign pre-test, before any division.  The oracle accepts a fragment iff b0, b1, b2 > 0 with
+    // b_i = fl(e_i / area) (then, PERSP, t_i = b_i z z / den).  While no quotient can underflow
+    // (|e_i| >= 1e-30, |area| < 1e6) the sign of fl(e_i / area) is the sign of e_i * area, so: without
+    // perspective correction a fragment whose e_i do not all carry area's sign is rejected; with it
+    // (all z > 0, so sign t_i = sign w_i and b_i = t_i / den) mixed signs are rejected and three
+    // negative w_i stay with the exact path (den < 0 makes all b_i positive - only possible for a
+    // sliver whose area changes sign when the epsilon is added).  Everything else: exact evaluation.
+    if (fabsf(e0) >= 1e-30f && fabsf(e1) >= 1e-30f && fabsf(e2) >= 1e-30f && fabsf(area) < 1e6f) {
+        const bool n0 = e0 < 0.f, n1 = e1 < 0.f, n2 = e2 < 0.f;
+        if (n0 != n1 || n1 != n2) return;
+        if (!PERSP) {
+            if (n0 != (area < 0.f)) return;
+            // depth to ~1e-6 relative without the IEEE divisions: clearly behind the stored depth -> out
+            const float pa = __fdividef(fmaf(e0, z0, fmaf(e1, z1, e2 * z2)), area);
+            if (pa * 0.99999f > cur) return;
+        }
+    }
+    FragEval fe = eval_fragment_e<PERSP>(e0, e1, e2, z0, z1, z2, area);
     if (!fe.ok) return;
     const float pz = fe.pz + 0.f;                               // -0 -> +0 so the bit pattern orders
     atomicMin(slot, ((unsigned long long)__float_as_uint(pz) << 32) | f);
@@ -429,6 +486,14 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     return inc - v;
 }
 
+// Fused backward of the fitting step (optional): gv_tile / gv_flag = this tile's share of d loss / d verts
+// (see the epilogue).
+struct FusedTail {
+    float* gv_tile;                  // (n_mesh, tiles, NVW*3) un-normalised vertex gradient of this tile, or null
+    int* gv_flag;                    // (n_mesh, tiles) 1 = gv_tile row written, 0 = tile carries no gradient
+};
+
+template <bool PERSP>
 __global__ void __launch_bounds__(RT_THREADS, 2)
 raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed,
@@ -436,7 +501,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
-                  float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop) {
+                  float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop, FusedTail tail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RasterSmem s = carve_smem(smem_raw, R, F);
     const int mesh = blockIdx.y;
@@ -527,7 +592,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         __syncwarp();                                         // candidate writes of all lanes visible
         for (int c = lane; c < n_cands; c += 32) {
             const unsigned int e = my_cands[c];
-            eval_and_commit(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0);
+            eval_and_commit<PERSP>(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0,
+                                   (e >> 25) & 1u);
         }
         n_cands = 0;
         __syncwarp();
@@ -545,7 +611,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         const int f = (fb + lane < F) ? (int)__ldg(face_order + fb + lane) : F;
         int ia = 0, ib = -1, ja = 0, jb = -1;
         float e_m[3] = {0.f, 0.f, 0.f}, e_c[3] = {0.f, 0.f, 0.f};
-        unsigned int e_flags = 0;          // bit i: edge i usable; bit 4 + i: edge i bounds the run from below (in x)
+        unsigned int e_flags = 0;          // bit i: edge i usable; bit 4 + i: edge i bounds the run from below (in x);
+                                           // bit 8: zmin is a lower bound of the face's depth (early z allowed)
         if (f < F) {
             const unsigned int pk = s.fp[f];
             const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
@@ -555,6 +622,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const float zmin = fminf(z0, fminf(z1, z2));
             const float farea = edge_rn(x0, y0, x1, y1, x2, y2);
             if (zmin >= EPS && !(farea <= EPS && farea >= -EPS)) {
+                if (PERSP || farea < 0.f || farea > 2e-4f) e_flags |= 256u;      // eps / A < 5e-5
                 const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
                 const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
                 ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
@@ -636,12 +704,12 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             int slot = warp_excl_scan(len, lane, &c_total);
             if (n_cands + c_total > RT_WCANDS) flush_cands();
             if (c_total > RT_WCANDS) {                           // very large faces: evaluate in place
-                for (int k = ka; k <= kb; ++k) eval_and_commit(s, fi, k, j, tx0, ty0);
+                for (int k = ka; k <= kb; ++k) eval_and_commit<PERSP>(s, fi, k, j, tx0, ty0, (o_fl >> 8) & 1u);
                 __syncwarp();
                 continue;
             }
             slot += n_cands;
-            const unsigned int base = fi | ((unsigned int)(j - ty0) << 11);
+            const unsigned int base = fi | ((unsigned int)(j - ty0) << 11) | ((o_fl & 256u) << 17);
             for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
             n_cands += c_total;
         }
@@ -654,14 +722,51 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     const float zmax = __fadd_rn(vw.zc, vw.zh), zmin_c = __fsub_rn(vw.zc, vw.zh);
     const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
     float l_sum = 0.f, l_cnt = 0.f;
+    // scratch carved from the (now dead) candidate lists
+    unsigned int* scratch = s.cands;
     // optional crop_hand of the rendered image before the loss (train_render.py:727): the stored
-    // image stays uncropped, only the loss (and its gradient, in the backward kernel) sees the crop
-    CropBox* cbox = reinterpret_cast<CropBox*>(s.cands);
+    // image stays uncropped, only the loss (and its gradient) sees the crop
+    CropBox* cbox = reinterpret_cast<CropBox*>(scratch);                            // words 0 .. 15
+    float* red = reinterpret_cast<float*>(scratch + 32);                            // 32 .. 95
+    int* qx = reinterpret_cast<int*>(scratch + 96);                                 // raster column of each tile column, minus q0x
+    int* qy = qx + RT_TW;                                                           // ... rows
+    unsigned long long* mom = reinterpret_cast<unsigned long long*>(scratch + 320); // (F) packed face moments
+    const int Fp = (F + 31) & ~31;
+    unsigned short* flist = reinterpret_cast<unsigned short*>(mom + Fp);            // per-warp lists of touched faces
+    float* sgn = reinterpret_cast<float*>(flist + Fp);                              // (NVW,3) NDC vertex gradients
     const bool do_crop = target && crop.joints;
-    if (do_crop) {
-        if (tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
-        __syncthreads();
+    // Fused backward (no perspective correction): the depth of a face is affine in the sample position,
+    // pz(p) = [z0 e0(p) + z1 e1(p) + z2 e2(p)] / area, so the whole zbuf cotangent of a face collapses to the
+    // three moments (sum g, sum g px, sum g py) over its pixels, and d loss / d img of the m2d loss is
+    // +-gk(hand) on the union mask.  The epilogue accumulates integer moments of sign(synth - real) per face -
+    // px = 1 - (2 q + 1) / S with the integer raster pixel q - packed into one 64-bit word (n << 48 |
+    // sum s dqy << 24 | sum s dqx, signed fields relative to the tile's first sample) and added with one native
+    // shared-memory atomic per run of equal faces; each warp then compacts its share of the face list to the
+    // touched faces, evaluates their closed-form gradient and scatters it to the vertices, and the vertices are
+    // chained through the projection.  The per-hand factor gk / zhalf is applied by the consumer (it needs the
+    // mask count of all tiles).  No pix_to_face plane, no second pass over target / img, no backward kernel.
+    const bool do_grad = !PERSP && tail.gv_tile != nullptr && target != nullptr;
+    if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
+    const float cx0s = s.xs[tx0], cy0s = s.ys[ty0];
+    const int q0x = (cx0s == cx0s) ? __float2int_rn(((1.f - cx0s) * vw.S - 1.f) * 0.5f) : 0;
+    const int q0y = (cy0s == cy0s) ? __float2int_rn(((1.f - cy0s) * vw.S - 1.f) * 0.5f) : 0;
+    if (do_grad) {
+        for (int i = tid; i < Fp; i += RT_THREADS) mom[i] = 0ull;
+        for (int i = tid; i < NVW * 3; i += RT_THREADS) sgn[i] = 0.f;
+        for (int i = tid; i < tw + th; i += RT_THREADS) {
+            const bool isx = i < tw;
+            const float c = isx ? s.xs[tx0 + i] : s.ys[ty0 + i - tw];
+            const int q = (c == c) ? __float2int_rn(((1.f - c) * vw.S - 1.f) * 0.5f) : 0;
+            if (isx) qx[i] = q - q0x; else qy[i - tw] = q - q0y;
+        }
     }
+    if (do_crop || do_grad) __syncthreads();
+    auto add_moments = [&](int f, int n, int mi, int dqy) {
+        if (f >= 0 && (n | mi) != 0) {
+            const long long v = ((long long)n << 48) + ((long long)(n * dqy) << 24) + (long long)mi;
+            atomicAdd(&mom[f], (unsigned long long)v);
+        }
+    };
     const bool fast = !zbuf && !bary && !dists && (R & 3) == 0 && (tw & 3) == 0;
     if (fast) {
         // default outputs only: four pixels per lane, 128-bit key / target loads and image stores;
@@ -676,12 +781,25 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                 if (target) tg = __ldg(reinterpret_cast<const float4*>(target + o));
                 const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
                 const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
-                const unsigned long long kk[4] = {k01.x, k01.y, k23.x, k23.y};
                 const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
+                if ((k01.x & k01.y & k23.x & k23.y) == ~0ull && !do_crop) {
+                    // four background pixels (the common case): far plane out, loss only where the target has depth
+                    if (target) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (tt[c] < thr || bgval < thr) { l_sum += fabsf(tt[c] - bgval); l_cnt += 1.f; }
+                    }
+                    *reinterpret_cast<float4*>(img + o) = make_float4(bgval, bgval, bgval, bgval);
+                    if (p2f) *reinterpret_cast<int4*>(p2f + o) = make_int4(-1, -1, -1, -1);
+                    continue;
+                }
+                const unsigned long long kk[4] = {k01.x, k01.y, k23.x, k23.y};
                 float v[4];
                 int ff[4];
+                int run_f = -1, run_n = 0, run_mi = 0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    bool grad_ok = false;                 // gates of the depth normalisation: bg fill and clamp pass no gradient
                     if (kk[c] == ~0ull) {
                         v[c] = bgval;
                         ff[c] = -1;
@@ -693,14 +811,30 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                         d = d < zmin_c ? zmin_c : d;
                         v[c] = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
                         ff[c] = (int)(unsigned int)(kk[c] & 0xffffffffu);
+                        grad_ok = z > 0.f && !(z > zmax) && !(z < zmin_c);
                     }
                     if (target) {
-                        const float vc = (do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh)) ? 1.f : v[c];
-                        if (tt[c] < thr || vc < thr) { l_sum += fabsf(tt[c] - vc); l_cnt += 1.f; }
+                        const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh));
+                        const float vc = kept ? v[c] : 1.f;
+                        const bool m = tt[c] < thr || vc < thr;
+                        if (m) { l_sum += fabsf(tt[c] - vc); l_cnt += 1.f; }
+                        if (do_grad && grad_ok && kept && m) {
+                            const float d = vc - tt[c];
+                            const int sg = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
+                            if (sg) {
+                                if (ff[c] != run_f) {
+                                    add_moments(run_f, run_n, run_mi, qy[ly]);
+                                    run_f = ff[c]; run_n = 0; run_mi = 0;
+                                }
+                                run_n += sg;
+                                run_mi += sg * qx[lx + c];
+                            }
+                        }
                     }
                 }
+                if (do_grad) add_moments(run_f, run_n, run_mi, qy[ly]);
                 *reinterpret_cast<float4*>(img + o) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<int4*>(p2f + o) = make_int4(ff[0], ff[1], ff[2], ff[3]);
+                if (p2f) *reinterpret_cast<int4*>(p2f + o) = make_int4(ff[0], ff[1], ff[2], ff[3]);
             }
         }
     } else
@@ -728,11 +862,18 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
             const float val = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
             img[o] = val;
-            p2f[o] = f;
+            if (p2f) p2f[o] = f;
             if (target) {
                 const float t = tg[q];
-                const float vc = (do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx, R, val, vw.zc, vw.zh)) ? 1.f : val;
-                if (t < thr || vc < thr) { l_sum += fabsf(t - vc); l_cnt += 1.f; }
+                const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx, R, val, vw.zc, vw.zh));
+                const float vc = kept ? val : 1.f;
+                const bool m = t < thr || vc < thr;
+                if (m) { l_sum += fabsf(t - vc); l_cnt += 1.f; }
+                if (do_grad && f >= 0 && kept && m && z > 0.f && !(z > zmax) && !(z < zmin_c)) {
+                    const float dd = vc - t;
+                    const int sg = dd > 0.f ? 1 : (dd < 0.f ? -1 : 0);
+                    add_moments(f, sg, sg * qx[lx], qy[ly]);
+                }
             }
             if (zbuf) zbuf[o] = z;
             if (bary || dists) {
@@ -745,7 +886,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                     const float x2 = s.vn[3 * i2], y2 = s.vn[3 * i2 + 1], z2 = s.vn[3 * i2 + 2];
                     const float px = s.xs[tx0 + lx], py = s.ys[ty0 + ly];
                     const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
-                    FragEval fe = eval_fragment(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
+                    FragEval fe = eval_fragment<PERSP>(px, py, x0, y0, z0, x1, y1, z1, x2, y2, z2, area);
                     b0 = fe.b0; b1 = fe.b1; b2 = fe.b2;
                     float d01 = seg_dist_rn(px, py, x0, y0, x1, y1);
                     float d02 = seg_dist_rn(px, py, x0, y0, x2, y2);
@@ -759,21 +900,77 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             }
         }
     }
-    if (parts_tile) {
-        // fixed-order block reduction (the lists are dead by now, reuse their storage)
-        float* red = reinterpret_cast<float*>(s.cands);
-        l_sum = warp_sum(l_sum);
-        l_cnt = warp_sum(l_cnt);
-        __syncthreads();
-        if (lane == 0) { red[2 * (tid >> 5)] = l_sum; red[2 * (tid >> 5) + 1] = l_cnt; }
-        __syncthreads();
-        if (tid == 0) {
-            float a = 0.f, b = 0.f;
-            for (int w = 0; w < RT_THREADS / 32; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
-            float* out = parts_tile + ((size_t)mesh * gridDim.x + tile) * 2;
-            out[0] = a;
-            out[1] = b;
+    if (do_grad) {
+        __syncthreads();                                      // moments complete
+        // each warp owns a contiguous share of the faces: compact it to the touched ones (ballot, no atomics),
+        // then one lane per touched face
+        const int share = (F + RT_THREADS / 32 - 1) / (RT_THREADS / 32);
+        const int f_lo = warp * share, f_hi = min(F, f_lo + share);
+        unsigned short* wl = flist + f_lo;
+        int cnt = 0;
+        for (int f0 = f_lo; f0 < f_hi; f0 += 32) {
+            const int f = f0 + lane;
+            const bool act = f < f_hi && mom[f] != 0ull;
+            const unsigned int mk = __ballot_sync(0xffffffffu, act);
+            if (act) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)f;
+            cnt += __popc(mk);
         }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+            const int f = wl[k];
+            // unpack the signed fields (low to high)
+            const long long pk64 = (long long)mom[f];
+            const int mi_r = (int)((pk64 << 40) >> 40);
+            const long long r1 = (pk64 - mi_r) >> 24;
+            const int mj_r = (int)((r1 << 40) >> 40);
+            const int n = (int)((r1 - mj_r) >> 24);
+            const int mi = mi_r + q0x * n, mj = mj_r + q0y * n;
+            const unsigned int pk = s.fp[f];
+            const int i0 = pk & 1023, i1 = (pk >> 10) & 1023, i2 = pk >> 20;
+            // float64 for the handful of operations per touched face: sliver faces amplify rounding by
+            // extent^2 / area, and the moments are exact integers worth keeping exact
+            const double x0 = s.vn[3 * i0], y0 = s.vn[3 * i0 + 1], z0 = s.vn[3 * i0 + 2];
+            const double ax = s.vn[3 * i1] - x0, ay = s.vn[3 * i1 + 1] - y0, dz1 = s.vn[3 * i1 + 2] - z0;
+            const double bx = s.vn[3 * i2] - x0, by = s.vn[3 * i2 + 1] - y0, dz2 = s.vn[3 * i2 + 2] - z0;
+            // U = sum s (p - v0) with p = 1 - (2 q + 1) / S: exact integer sums, scaled once
+            const double inv_S = 1.0 / (double)vw.S, S0 = (double)n;
+            const double Ux = S0 * (1.0 - inv_S - x0) - 2.0 * inv_S * (double)mi;
+            const double Uy = S0 * (1.0 - inv_S - y0) - 2.0 * inv_S * (double)mj;
+            double g[9];
+            face_grad<double>(z0, ax, ay, dz1, bx, by, dz2, S0, Ux, Uy, g);
+            atomicAdd(&sgn[3 * i0], (float)g[0]); atomicAdd(&sgn[3 * i0 + 1], (float)g[1]); atomicAdd(&sgn[3 * i0 + 2], (float)g[2]);
+            atomicAdd(&sgn[3 * i1], (float)g[3]); atomicAdd(&sgn[3 * i1 + 1], (float)g[4]); atomicAdd(&sgn[3 * i1 + 2], (float)g[5]);
+            atomicAdd(&sgn[3 * i2], (float)g[6]); atomicAdd(&sgn[3 * i2 + 1], (float)g[7]); atomicAdd(&sgn[3 * i2 + 2], (float)g[8]);
+        }
+        const int tile_has = __syncthreads_or(cnt > 0 ? 1 : 0);
+        const size_t slot = (size_t)mesh * gridDim.x + tile;
+        if (tid == 0) tail.gv_flag[slot] = tile_has;
+        if (tile_has) {
+            float* go = tail.gv_tile + slot * NVW * 3;
+            float sxp = 1.f, syp = 1.f, szp = 1.f;
+            if (ps) { sxp = ps[0] * 0.5f; syp = ps[1] * 0.5f; szp = ps[2] * 0.5f; }
+            for (int v = tid; v < NVW; v += RT_THREADS) {
+                const float gxn = sgn[3 * v], gyn = sgn[3 * v + 1], gzn = sgn[3 * v + 2];
+                // x_ndc = -fxn x / z + pxn (same for y), z_ndc = z; fxn x / z = pxn - x_ndc
+                const float xn = s.vn[3 * v], yn = s.vn[3 * v + 1], iz = 1.f / s.vn[3 * v + 2];
+                go[3 * v] = -gxn * vw.fxn * iz * sxp;
+                go[3 * v + 1] = -gyn * vw.fyn * iz * syp;
+                go[3 * v + 2] = (gzn + (gxn * (vw.pxn - xn) + gyn * (vw.pyn - yn)) * iz) * szp;
+            }
+        }
+    }
+    if (!parts_tile) return;
+    // fixed-order block reduction of the tile's loss sums (the consumers fold the tiles of a mesh)
+    l_sum = warp_sum(l_sum);
+    l_cnt = warp_sum(l_cnt);
+    if (lane == 0) { red[2 * warp] = l_sum; red[2 * warp + 1] = l_cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < RT_THREADS / 32; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+        float* out = parts_tile + ((size_t)mesh * gridDim.x + tile) * 2;
+        out[0] = a;
+        out[1] = b;
     }
 }
 
@@ -783,44 +980,60 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
                             const float* target, float thr, float* parts_tile, const CropParams* crop,
-                            cudaStream_t st) {
+                            int flags, const RasterFused* fused, cudaStream_t st) {
     if (h->n_faces > RT_MAXF) {
         dsf_set_error("rasteriser supports at most %d faces (got %d)", RT_MAXF, h->n_faces);
         return DSF_ERR_UNSUPPORTED;
     }
+    const bool persp = (flags & DSF_RASTER_PERSPECTIVE_CORRECT) != 0;
     const int tiles_x = (R + RT_TW - 1) / RT_TW, tiles_y = (R + RT_TH - 1) / RT_TH;
     const size_t smem = raster_fwd_smem(R, h->n_faces);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 16 || !attr_set[dev]) {
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
         if (dev < 16) attr_set[dev] = true;
+    }
+    FusedTail tail = {};
+    if (fused && fused->gv_tile && dsf_raster_fused_grad_ok(h, flags)) {
+        tail.gv_tile = fused->gv_tile;
+        tail.gv_flag = fused->gv_flag;
     }
     // bulk (TMA) staging needs 16-byte aligned sources and sizes; anything else takes plain loads
     const int use_tma = (R % 4 == 0) && ((uintptr_t)verts % 16 == 0) && ((uintptr_t)xs % 16 == 0) &&
                         ((uintptr_t)ys % 16 == 0);
     dim3 grid(tiles_x * tiles_y, n_mesh);
-    raster_fwd_kernel<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off,
-                                                      h->faces_packed, h->face_order, h->n_faces, view, xs, ys, img, p2f,
-                                                      zbuf, bary, dists, target, thr, parts_tile, use_tma,
-                                                      crop ? *crop : CropParams{});
+    auto kern = persp ? raster_fwd_kernel<true> : raster_fwd_kernel<false>;
+    kern<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off, h->faces_packed, h->face_order,
+                                         h->n_faces, view, xs, ys, img, p2f, zbuf, bary, dists, target, thr,
+                                         parts_tile, use_tma, crop ? *crop : CropParams{}, tail);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
+}
+
+// can the forward epilogue produce the vertex gradient itself (see raster_fwd_kernel)?  Needs the affine depth of
+// the non-perspective-correct rasteriser (the scratch tables fit the candidate-list storage for any F <= RT_MAXF).
+bool dsf_raster_fused_grad_ok(const DsfMano* h, int flags) {
+    (void)h;
+    return !(flags & (DSF_RASTER_PERSPECTIVE_CORRECT | DSF_RASTER_SEPARATE_BACKWARD));
 }
 
 extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                                   const float* xs, const float* ys, int R, float* img, int* pix_to_face,
                                   float* zbuf, float* bary, float* dists, const float* target, float thr,
-                                  float* loss_parts_tile, dsfStream_t stream) {
+                                  float* loss_parts_tile, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && verts_cam && view && xs && ys && img && pix_to_face, "null argument");
     DSF_REQUIRE(!target == !loss_parts_tile, "target and loss_parts_tile go together");
     DSF_REQUIRE(n_mesh > 0 && n_mesh <= 65535, "n_mesh must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face,
-                                   zbuf, bary, dists, target, thr, loss_parts_tile, nullptr, (cudaStream_t)stream);
+                                   zbuf, bary, dists, target, thr, loss_parts_tile, nullptr, flags, nullptr,
+                                   (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,14 +1047,14 @@ extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* ver
 
 // RB_THREADS: 256 keeps more CTAs (hands) in flight for large batches, 512 halves the per-hand latency
 // when the batch does not fill the GPU anyway
-template <int RB_THREADS>
+template <int RB_THREADS, bool PERSP>
 __global__ void __launch_bounds__(RB_THREADS, RB_THREADS == 256 ? 6 : 2)     // 40 registers: 6 CTAs (48 warps) per SM
 raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const int* __restrict__ faces,
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   const int* __restrict__ p2f, const float* __restrict__ g_img, float* __restrict__ g_verts,
                   const float* __restrict__ target, const float* __restrict__ img,
-                  const float* __restrict__ parts, float gscale, float thr, CropParams crop) {
+                  const float* __restrict__ parts_tile, int n_tiles, float gscale, float thr, CropParams crop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* svn = reinterpret_cast<float*>(smem_raw);
     float* sgn = svn + NVW * 3;
@@ -874,7 +1087,10 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     const float* gi = g_img ? g_img + (size_t)mesh * R * R : nullptr;
     const float* tg = target ? target + (size_t)mesh * R * R : nullptr;
     const float* im = img ? img + (size_t)mesh * R * R : nullptr;
-    const float gk = parts ? gscale / (parts[2 * mesh + 1] + 1e-8f) : 0.f;
+    float n_mask = 0.f;                                    // mask count of the mesh = sum over its tiles
+    if (parts_tile)
+        for (int t = 0; t < n_tiles; ++t) n_mask += parts_tile[((size_t)mesh * n_tiles + t) * 2 + 1];
+    const float gk = parts_tile ? gscale / (n_mask + 1e-8f) : 0.f;
     __shared__ CropBox cbox;
     const bool do_crop = !gi && crop.joints;
     if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, &cbox);
@@ -895,6 +1111,7 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
     __shared__ int s_count;
     const int lane = tid & 31;
     const int n_pix = R * R;
+    const bool pf_vec = (reinterpret_cast<uintptr_t>(pf) & 15) == 0;   // odd R: planes after the first are unaligned
     constexpr int RB_CHUNK = RB_CHUNK_OF(RB_THREADS);
     for (int chunk0 = 0; chunk0 < n_pix; chunk0 += RB_CHUNK) {
       const int chunk_n = min(RB_CHUNK, n_pix - chunk0);
@@ -903,12 +1120,13 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
       for (int q0 = (tid & ~31) * 4; q0 < chunk_n; q0 += RB_THREADS * 4) {
           const int k0 = q0 + lane * 4;                          // 4 consecutive pixels per lane
           int4 f4 = make_int4(-1, -1, -1, -1);
-          if (k0 + 3 < chunk_n) {
-              f4 = *reinterpret_cast<const int4*>(pf + chunk0 + k0);   // R*R is a multiple of 4
+          if (k0 + 3 < chunk_n && pf_vec) {
+              f4 = *reinterpret_cast<const int4*>(pf + chunk0 + k0);   // plane 16-byte aligned (R*R % 4 == 0)
           } else {
               if (k0 < chunk_n) f4.x = pf[chunk0 + k0];
               if (k0 + 1 < chunk_n) f4.y = pf[chunk0 + k0 + 1];
               if (k0 + 2 < chunk_n) f4.z = pf[chunk0 + k0 + 2];
+              if (k0 + 3 < chunk_n) f4.w = pf[chunk0 + k0 + 3];
           }
           const int n = (f4.x >= 0) + (f4.y >= 0) + (f4.z >= 0) + (f4.w >= 0);
           int total;
@@ -940,32 +1158,41 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
         const float e0 = edge_rn(px, py, x1, y1, x2, y2);
         const float e1 = edge_rn(px, py, x2, y2, x0, y0);
         const float e2 = edge_rn(px, py, x0, y0, x1, y1);
-        const float ia = 1.f / area;
-        const float w0 = e0 * ia, w1 = e1 * ia, w2 = e2 * ia;
-        const float t0 = w0 * z1 * z2, t1 = z0 * w1 * z2, t2 = z0 * z1 * w2;
-        const float den = t0 + t1 + t2;
-        const float id = 1.f / den;
-        const float b0 = t0 * id, b1 = t1 * id, b2 = t2 * id;
-        const float pz = b0 * z0 + b1 * z1 + b2 * z2;
-        // gates of the forward epilogue: background fill and the [zmin,zmax] clamp pass no gradient
-        act = act && g != 0.f && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
-        const float gz = act ? g * inv_zh : 0.f;
-        const float gb0 = gz * z0, gb1 = gz * z1, gb2 = gz * z2;
-        const float sgb = (gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
-        const float gt0 = gb0 * id - sgb, gt1 = gb1 * id - sgb, gt2 = gb2 * id - sgb;
-        const float gw0 = gt0 * z1 * z2, gw1 = gt1 * z0 * z2, gw2 = gt2 * z0 * z1;
-        const float ge0 = gw0 * ia, ge1 = gw1 * ia, ge2 = gw2 * ia;
-        const float garea = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * ia * ia;
         float gv[9];
-        gv[0] = ge1 * (y2 - py) + ge2 * (py - y1) + garea * (y2 - y1);
-        gv[1] = ge1 * (px - x2) + ge2 * (x1 - px) + garea * (x1 - x2);
-        gv[2] = gz * b0 + gt1 * w1 * z2 + gt2 * z1 * w2;
-        gv[3] = ge0 * (py - y2) + ge2 * (y0 - py) + garea * (y0 - y2);
-        gv[4] = ge0 * (x2 - px) + ge2 * (px - x0) + garea * (x2 - x0);
-        gv[5] = gz * b1 + gt0 * w0 * z2 + gt2 * z0 * w2;
-        gv[6] = ge0 * (y1 - py) + ge1 * (py - y0) + garea * (y1 - y0);
-        gv[7] = ge0 * (px - x1) + ge1 * (x0 - px) - garea * (x1 - x0);
-        gv[8] = gz * b2 + gt0 * w0 * z1 + gt1 * z0 * w1;
+        if (PERSP) {
+            const float ia = 1.f / area;
+            const float w0 = e0 * ia, w1 = e1 * ia, w2 = e2 * ia;
+            const float t0 = w0 * z1 * z2, t1 = z0 * w1 * z2, t2 = z0 * z1 * w2;
+            const float id = 1.f / (t0 + t1 + t2);
+            const float b0 = t0 * id, b1 = t1 * id, b2 = t2 * id;
+            const float pz = b0 * z0 + b1 * z1 + b2 * z2;
+            // gates of the forward epilogue: background fill and the [zmin,zmax] clamp pass no gradient
+            act = act && g != 0.f && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
+            const float gz = act ? g * inv_zh : 0.f;
+            const float gb0 = gz * z0, gb1 = gz * z1, gb2 = gz * z2;
+            const float sgb = (gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
+            const float gt0 = gb0 * id - sgb, gt1 = gb1 * id - sgb, gt2 = gb2 * id - sgb;
+            const float gw0 = gt0 * z1 * z2, gw1 = gt1 * z0 * z2, gw2 = gt2 * z0 * z1;
+            const float ge0 = gw0 * ia, ge1 = gw1 * ia, ge2 = gw2 * ia;
+            const float garea = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * ia * ia;
+            gv[0] = ge1 * (y2 - py) + ge2 * (py - y1) + garea * (y2 - y1);
+            gv[1] = ge1 * (px - x2) + ge2 * (x1 - px) + garea * (x1 - x2);
+            gv[2] = gz * b0 + gt1 * w1 * z2 + gt2 * z1 * w2;
+            gv[3] = ge0 * (py - y2) + ge2 * (y0 - py) + garea * (y0 - y2);
+            gv[4] = ge0 * (x2 - px) + ge2 * (px - x0) + garea * (x2 - x0);
+            gv[5] = gz * b1 + gt0 * w0 * z2 + gt2 * z0 * w2;
+            gv[6] = ge0 * (y1 - py) + ge1 * (py - y0) + garea * (y1 - y0);
+            gv[7] = ge0 * (px - x1) + ge1 * (x0 - px) - garea * (x1 - x0);
+            gv[8] = gz * b2 + gt0 * w0 * z1 + gt1 * z0 * w1;
+        } else {
+            // screen-space interpolation: the face's depth is affine in p, use the well-conditioned closed form
+            // (face_grad) per pixel with S0 = gz, U = gz (p - v0)
+            const float ia = 1.f / area;
+            const float pz = (e0 * z0 + e1 * z1 + e2 * z2) * ia;
+            act = act && g != 0.f && (pz > 0.f) && !(pz > zmax) && !(pz < zmin_c);
+            const float gz = act ? g * inv_zh : 0.f;
+            face_grad<float>(z0, x1 - x0, y1 - y0, z1 - z0, x2 - x0, y2 - y0, z2 - z0, gz, gz * (px - x0), gz * (py - y0), gv);
+        }
         // Neighbouring pixels mostly hit the same face, and float atomics on shared memory are CAS
         // loops that serialise on equal addresses: sum each run of equal face ids inside the warp
         // (segmented scan) and let only the last lane of a run touch shared memory.
@@ -1011,8 +1238,9 @@ raster_bwd_kernel(int R, const float* __restrict__ verts, const float* __restric
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,
-                             const float* img, const float* parts, float gscale, float thr, const CropParams* crop,
-                             cudaStream_t st) {
+                             const float* img, const float* parts_tile, float gscale, float thr, const CropParams* crop,
+                             int flags, cudaStream_t st) {
+    const bool persp = (flags & DSF_RASTER_PERSPECTIVE_CORRECT) != 0;
     const int rb_threads = n_mesh < 2048 ? 512 : 256;
     const size_t smem = (size_t)NVW * 3 * 4 * 2 + (size_t)2 * R * 4 + (size_t)RB_CHUNK_OF(rb_threads) * 2;
     const int max_smem = (int)((size_t)NVW * 3 * 4 * 2 + (size_t)2 * RT_MAXR * 4 + (size_t)RB_CHUNK_OF(512) * 2);
@@ -1020,31 +1248,30 @@ int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, c
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 16 || !attr_set[dev]) {
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_bwd_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         if (dev < 16) attr_set[dev] = true;
     }
-    if (n_mesh < 2048)
-        raster_bwd_kernel<512><<<n_mesh, 512, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
-                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr,
-                                                          crop ? *crop : CropParams{});
-    else
-        raster_bwd_kernel<256><<<n_mesh, 256, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys,
-                                                          p2f, g_img, g_verts, target, img, parts, gscale, thr,
-                                                          crop ? *crop : CropParams{});
+    auto kern = rb_threads == 512 ? (persp ? raster_bwd_kernel<512, true> : raster_bwd_kernel<512, false>)
+                                  : (persp ? raster_bwd_kernel<256, true> : raster_bwd_kernel<256, false>);
+    kern<<<n_mesh, rb_threads, smem, st>>>(R, verts, place_scale, place_off, h->faces, view, xs, ys, p2f, g_img,
+                                           g_verts, target, img, parts_tile, dsf_raster_tiles(R), gscale, thr,
+                                           crop ? *crop : CropParams{});
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
 
 extern "C" int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                                    const float* xs, const float* ys, int R, const int* pix_to_face,
-                                   const float* g_img, float* g_verts_cam, dsfStream_t stream) {
+                                   const float* g_img, float* g_verts_cam, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
     DSF_REQUIRE(h && verts_cam && view && xs && ys && pix_to_face && g_img && g_verts_cam, "null argument");
     DSF_REQUIRE(n_mesh > 0, "n_mesh must be positive");
     DSF_REQUIRE(R >= 8 && R <= RT_MAXR, "crop size R must be in [8,512]");
     return dsf_raster_backward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, pix_to_face,
-                                    g_img, g_verts_cam, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr,
+                                    g_img, g_verts_cam, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, flags,
                                     (cudaStream_t)stream);
 }
 
@@ -1129,29 +1356,6 @@ depth_loss_grad_global_kernel(int n, const float* __restrict__ real, const float
     }
 }
 
-// fold per-tile partial sums (written by the fused raster epilogue) into parts (B,2), fixed order
-__global__ void __launch_bounds__(LS_THREADS)
-fold_tile_parts_kernel(int B, int n_tiles, const float* __restrict__ parts_tile, float* __restrict__ parts) {
-    const int b = blockIdx.x * LS_THREADS + threadIdx.x;
-    if (b >= B) return;
-    float s = 0.f, c = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-        s += parts_tile[((size_t)b * n_tiles + t) * 2];
-        c += parts_tile[((size_t)b * n_tiles + t) * 2 + 1];
-    }
-    parts[2 * b] = s;
-    parts[2 * b + 1] = c;
-}
-
-int dsf_fold_loss_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
-                       cudaStream_t st) {
-    fold_tile_parts_kernel<<<(B + LS_THREADS - 1) / LS_THREADS, LS_THREADS, 0, st>>>(B, n_tiles, parts_tile, parts);
-    DSF_CHECK_LAUNCH();
-    depth_loss_totals_kernel<<<1, LS_THREADS, 0, st>>>(0, B, weight, parts, totals);
-    DSF_CHECK_LAUNCH();
-    return DSF_OK;
-}
-
 int dsf_depth_loss_impl(int mode, int B, int R, const float* real, const float* synth, float thr, float weight,
                         float* parts, float* totals, float* g_synth, cudaStream_t st) {
     const int n = R * R;
@@ -1163,6 +1367,53 @@ int dsf_depth_loss_impl(int mode, int B, int R, const float* real, const float* 
         depth_loss_grad_global_kernel<<<B, LS_THREADS, 0, st>>>(n, real, synth, thr, totals, g_synth);
         DSF_CHECK_LAUNCH();
     }
+    return DSF_OK;
+}
+
+// parts (B,2) from the per-tile sums + totals (4): one CTA, for the stand-alone dsf_raster_loss_grad
+__global__ void __launch_bounds__(LS_THREADS)
+fold_totals_kernel(int B, int n_tiles, float weight, const float* __restrict__ parts_tile, float* __restrict__ parts,
+                   float* __restrict__ totals) {
+    __shared__ float red[LS_THREADS / 32][2];
+    __shared__ float red2[LS_THREADS / 32][2];
+    float sum = 0.f, cnt = 0.f, per = 0.f;
+    for (int b = threadIdx.x; b < B; b += LS_THREADS) {
+        float a = 0.f, c = 0.f;
+        for (int t = 0; t < n_tiles; ++t) {
+            a += parts_tile[((size_t)b * n_tiles + t) * 2];
+            c += parts_tile[((size_t)b * n_tiles + t) * 2 + 1];
+        }
+        parts[2 * b] = a; parts[2 * b + 1] = c;
+        sum += a; cnt += c; per += a / (c + 1e-8f);
+    }
+    float2 t = block_sum2(sum, cnt, red);
+    float2 u = block_sum2(per, 0.f, red2);
+    if (threadIdx.x == 0) {
+        totals[0] = weight * u.x / (float)B; totals[1] = t.x; totals[2] = t.y; totals[3] = weight * u.x;
+    }
+}
+
+int dsf_fold_totals_impl(int B, int n_tiles, float weight, const float* parts_tile, float* parts, float* totals,
+                         cudaStream_t st) {
+    fold_totals_kernel<<<1, LS_THREADS, 0, st>>>(B, n_tiles, weight, parts_tile, parts, totals);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// totals of a batch that was processed as n_slices separate dsf_fit_step calls (parallel streams):
+// [3] (un-normalised loss), [1], [2] add up; [0] = sum [3] / norm_batch
+__global__ void sum_totals_kernel(int n, const float* __restrict__ slice_totals, float norm, float* __restrict__ totals) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < n; ++i) { a += slice_totals[4 * i + 1]; b += slice_totals[4 * i + 2]; c += slice_totals[4 * i + 3]; }
+    totals[0] = c / norm; totals[1] = a; totals[2] = b; totals[3] = c;
+}
+
+extern "C" int dsf_sum_totals(int n_slices, const float* slice_totals, int norm_batch, float* totals,
+                              dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(n_slices > 0 && slice_totals && totals && norm_batch > 0, "bad argument");
+    sum_totals_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_slices, slice_totals, (float)norm_batch, totals);
+    DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
 

@@ -13,9 +13,25 @@ from . import _lib as L
 
 
 class FitStep:
+    """One fitting step over a resident batch.
+
+    perspective_correct: pytorch3d's RasterizationSettings flag; False (default) is what the reference runs
+    with (pytorch3d 0.4.0 default, see include/dsf_b200.h).  keep_pix_to_face=False drops the pix_to_face
+    plane, which nothing reads once the rasteriser emits the vertex gradient itself (default settings only).
+    The per-hand view records depend only on (center3d, cube): they are rebuilt by set_inputs(), not by
+    every step()."""
+
     def __init__(self, mano_layer, batch, crop=128, cam_para=(588.03, 587.07, 320.0, 240.0),
-                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None, chunks=1):
+                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None, chunks=1,
+                 perspective_correct=False, keep_pix_to_face=True):
         self.lib = L.lib()
+        self.flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
+        if mode != "direct":
+            # literal 640-pixel raster: float32 sample coordinates are not exactly 1 - (2 q + 1) / S there, keep
+            # the per-pixel backward kernel (see DSF_RASTER_SEPARATE_BACKWARD)
+            self.flags |= L.RASTER_SEPARATE_BACKWARD
+        if self.flags and not keep_pix_to_face:
+            raise ValueError("only the direct-mode, non-perspective-correct step can drop the pix_to_face plane")
         self.layer = mano_layer
         self.B, self.R = int(batch), int(crop)
         self.mode = 0 if mode == "direct" else 1
@@ -35,7 +51,7 @@ class FitStep:
         self.ys = f(B, R)
         self.M = f(B, 3, 3)
         self.img = f(B, R, R)
-        self.p2f = torch.empty(B, R, R, dtype=torch.int32, device=dev)
+        self.p2f = torch.empty(B, R, R, dtype=torch.int32, device=dev) if keep_pix_to_face else None
         self.verts = f(B, L.NVW, 3)
         self.joints = f(B, L.NJOUT, 3)
         self.g_params = f(B, 62)
@@ -57,12 +73,20 @@ class FitStep:
         self.use_graph = use_graph
         self._graph = None
         self.launches_per_step = 0
+        self.setup_launches = 0
 
     # inputs already resident in HBM -----------------------------------------------------------------
+    def _view_setup(self):
+        L.check(self.lib.dsf_view_setup(self.mode, self.B, self.center3d.data_ptr(), self.cube.data_ptr(),
+                                        self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
+                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), L.stream_ptr()))
+        self.setup_launches = self.lib.dsf_last_launch_count()
+
     def set_inputs(self, params, center3d, cube, target=None):
         self.params.copy_(params, non_blocking=True)
         self.center3d.copy_(center3d, non_blocking=True)
         self.cube.copy_(cube, non_blocking=True)
+        self._view_setup()                       # view records / sample grids follow (center3d, cube)
         if target is not None:
             if target.dtype == torch.uint16:
                 # sensor format: uint16 millimetres travel over PCIe (half the bytes), normalised here
@@ -78,18 +102,19 @@ class FitStep:
     def set_crop_joints(self, joints):
         """Teacher joints (B,J,3) in normalised cube units: the rendered image is passed through
         crop_hand (data/render_loader.py:1209) before the m2d loss, as train_render.py:727 does.
-        Call before the first step (the pointer is baked into the captured graph)."""
+        The teacher joints change with every batch (train_render.py:727): later calls with the same shape
+        copy into the buffer the captured graph reads; only enabling cropping, or changing the joint count,
+        after capture is refused."""
+        joints = L.f32c(joints)
+        if self.crop_joints is not None and tuple(self.crop_joints.shape) == tuple(joints.shape):
+            self.crop_joints.copy_(joints, non_blocking=True)
+            return
         if self._graph is not None:
-            raise RuntimeError("set_crop_joints must be called before the CUDA graph is captured")
-        self.crop_joints = L.f32c(joints).clone()
+            raise RuntimeError("crop joints must first be set (and keep their shape) before the CUDA graph is captured")
+        self.crop_joints = joints.clone()
 
     def _enqueue(self):
-        s = L.stream_ptr()
         n = 0
-        L.check(self.lib.dsf_view_setup(self.mode, self.B, self.center3d.data_ptr(), self.cube.data_ptr(),
-                                        self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
-                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), s))
-        n += self.lib.dsf_last_launch_count()
         nj = 0 if self.crop_joints is None else self.crop_joints.shape[1]
         R2 = self.R * self.R
 
@@ -101,9 +126,10 @@ class FitStep:
                 off(self.cube, 3), off(self.view, L.VIEW_STRIDE), off(self.xs, self.R), off(self.ys, self.R),
                 off(self.target, R2), self.loss_weight, self.B,
                 None if self.crop_joints is None else off(self.crop_joints, nj * 3), nj, off(self.M, 9),
-                self._intr, off(self.img, R2), off(self.p2f, R2), off(self.verts, L.NVW * 3),
-                off(self.joints, L.NJOUT * 3), off(self.g_params, 62), off(self.parts, 2),
-                self.chunk_totals[c].data_ptr(), self.ws[c].data_ptr(), L.stream_ptr()))
+                self._intr, off(self.img, R2), None if self.p2f is None else off(self.p2f, R2),
+                off(self.verts, L.NVW * 3), off(self.joints, L.NJOUT * 3), off(self.g_params, 62), off(self.parts, 2),
+                self.totals.data_ptr() if self.chunks == 1 else self.chunk_totals[c].data_ptr(),
+                self.ws[c].data_ptr(), self.flags, L.stream_ptr()))
             return self.lib.dsf_last_launch_count()
 
         main = torch.cuda.current_stream()
@@ -114,12 +140,11 @@ class FitStep:
         n += run_chunk(0)
         for st in self._streams:                                # join
             main.wait_stream(st)
-        # totals of the whole batch from the per-slice records ([3] is the un-normalised loss)
-        if self.chunks == 1:
-            self.totals.copy_(self.chunk_totals[0])
-        else:
-            ssum = self.chunk_totals.sum(0)
-            self.totals.copy_(torch.stack([ssum[3] / self.B, ssum[1], ssum[2], ssum[3]]))
+        if self.chunks > 1:
+            # totals of the whole batch from the per-slice records ([3] is the un-normalised loss)
+            L.check(self.lib.dsf_sum_totals(self.chunks, self.chunk_totals.data_ptr(), self.B,
+                                            self.totals.data_ptr(), L.stream_ptr()))
+            n += self.lib.dsf_last_launch_count()
         self.launches_per_step = n
 
     def step(self):
@@ -142,6 +167,7 @@ class FitStep:
         keep = self.params.clone()
         self.params.copy_(params_target)
         self.target.fill_(1.0)
+        self._view_setup()
         self._enqueue()
         self.target.copy_(self.img)
         self.params.copy_(keep)
@@ -154,8 +180,14 @@ class MultiViewFitStep:
     Buffers are persistent; the launch sequence is replayed as a CUDA graph."""
 
     def __init__(self, mano_layer, batch, views, crop=256, cam_para=(588.03, 587.07, 320.0, 240.0),
-                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None):
+                 image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None,
+                 perspective_correct=False, keep_pix_to_face=True):
         self.lib = L.lib()
+        self.flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
+        if mode != "direct":
+            self.flags |= L.RASTER_SEPARATE_BACKWARD
+        if self.flags and not keep_pix_to_face:
+            raise ValueError("only the direct-mode, non-perspective-correct step can drop the pix_to_face plane")
         self.layer = mano_layer
         self.B, self.V, self.R = int(batch), int(views), int(crop)
         self.mode = 0 if mode == "direct" else 1
@@ -171,7 +203,7 @@ class MultiViewFitStep:
         self.view, self.xs, self.ys, self.M = f(B * V, L.VIEW_STRIDE), f(B * V, R), f(B * V, R), f(B * V, 3, 3)
         self._c3v, self._cubev = f(B * V, 3), f(B * V, 3)
         self.img = f(B * V, R, R)
-        self.p2f = torch.empty(B * V, R, R, dtype=torch.int32, device=dev)
+        self.p2f = torch.empty(B * V, R, R, dtype=torch.int32, device=dev) if keep_pix_to_face else None
         self.verts, self.joints = f(B, L.NVW, 3), f(B, L.NJOUT, 3)
         self.g_params = f(B, 62)
         self.parts, self.totals = f(B * V, 2), f(4)
@@ -193,22 +225,32 @@ class MultiViewFitStep:
         self.rot.copy_(rot)
         self._c3v.copy_(self.center3d.repeat_interleave(self.V, 0))
         self._cubev.copy_(self.cube.repeat_interleave(self.V, 0))
+        self._view_setup()
         if target is not None:
             self.target.copy_(target.reshape(self.B * self.V, self.R, self.R), non_blocking=True)
 
-    def _enqueue(self):
-        s = L.stream_ptr()
+    def _view_setup(self):
         L.check(self.lib.dsf_view_setup(self.mode, self.B * self.V, self._c3v.data_ptr(), self._cubev.data_ptr(),
                                         self._intr, self.W, self.H, self.R, None, self.view.data_ptr(),
-                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), s))
-        n = self.lib.dsf_last_launch_count()
+                                        self.xs.data_ptr(), self.ys.data_ptr(), self.M.data_ptr(), L.stream_ptr()))
+
+    def _enqueue(self):
+        s = L.stream_ptr()
         L.check(self.lib.dsf_fit_step_views(
             self.layer._handle, self.B, self.V, self.R, self.params.data_ptr(), self.center3d.data_ptr(),
             self.cube.data_ptr(), self.rot.data_ptr(), self.view.data_ptr(), self.xs.data_ptr(), self.ys.data_ptr(),
-            self.target.data_ptr(), self.loss_weight, self.img.data_ptr(), self.p2f.data_ptr(), self.verts.data_ptr(),
+            self.target.data_ptr(), self.loss_weight, self.img.data_ptr(), L.ptr(self.p2f), self.verts.data_ptr(),
             self.joints.data_ptr(), self.g_params.data_ptr(), self.parts.data_ptr(), self.totals.data_ptr(),
-            self.ws.data_ptr(), s))
-        self.launches_per_step = n + self.lib.dsf_last_launch_count()
+            self.ws.data_ptr(), self.flags, s))
+        self.launches_per_step = self.lib.dsf_last_launch_count()
+
+    @property
+    def verts_cam(self):
+        """(B*V,779,3) camera-space vertices of every view, as the last step left them in the workspace
+        (layout of dsf_fit_step_views: MANO scratch | g_verts | verts_cam | ...)."""
+        off = self.B * (self.lib.dsf_mano_workspace_floats(1) + L.NVW * 3)
+        n = self.B * self.V * L.NVW * 3
+        return self.ws[off:off + n].view(self.B * self.V, L.NVW, 3)
 
     def step(self):
         if not self.use_graph:

@@ -110,7 +110,7 @@ class _RasterFunction(torch.autograd.Function):
     """Normalised depth image from camera-space vertices (dsf_raster_forward / _backward)."""
 
     @staticmethod
-    def forward(ctx, layer, verts_cam, view, xs, ys):
+    def forward(ctx, layer, verts_cam, view, xs, ys, flags=0):
         lib = L.lib()
         verts_cam = L.f32c(verts_cam)
         NM = verts_cam.shape[0]
@@ -120,8 +120,9 @@ class _RasterFunction(torch.autograd.Function):
         p2f = torch.empty(NM, R, R, dtype=torch.int32, device=dev)
         L.check(lib.dsf_raster_forward(layer._handle, NM, verts_cam.data_ptr(), view.data_ptr(), xs.data_ptr(),
                                        ys.data_ptr(), R, img.data_ptr(), p2f.data_ptr(), None, None, None,
-                                       None, 0.0, None, L.stream_ptr()))
+                                       None, 0.0, None, flags, L.stream_ptr()))
         ctx.layer = layer
+        ctx.flags = flags
         ctx.save_for_backward(verts_cam, view, xs, ys, p2f)
         ctx.mark_non_differentiable(p2f)
         return img, p2f
@@ -136,8 +137,8 @@ class _RasterFunction(torch.autograd.Function):
         gv = torch.empty_like(verts_cam)
         L.check(lib.dsf_raster_backward(ctx.layer._handle, NM, verts_cam.data_ptr(), view.data_ptr(),
                                         xs.data_ptr(), ys.data_ptr(), R, p2f.data_ptr(), g_img.data_ptr(),
-                                        gv.data_ptr(), L.stream_ptr()))
-        return None, gv, None, None, None
+                                        gv.data_ptr(), ctx.flags, L.stream_ptr()))
+        return None, gv, None, None, None, None
 
 
 class _CollFunction(torch.autograd.Function):
@@ -394,7 +395,8 @@ class _RenderFunction(torch.autograd.Function):
         L.check(lib.dsf_render_forward(layer._handle, B, R, prm.data_ptr(), ld, qd, center3d.data_ptr(),
                                        cube_size.data_ptr(), view.data_ptr(), xs.data_ptr(), ys.data_ptr(), M.data_ptr(),
                                        render._intr, img.data_ptr(), p2f.data_ptr(), verts.data_ptr(), joints.data_ptr(),
-                                       juvd.data_ptr(), jxyz.data_ptr(), mxyz.data_ptr(), ws.data_ptr(), L.stream_ptr()))
+                                       juvd.data_ptr(), jxyz.data_ptr(), mxyz.data_ptr(), ws.data_ptr(),
+                                       render.raster_flags, L.stream_ptr()))
         ctx.render = render
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
         ctx.save_for_backward(prm, center3d, cube_size, view, xs, ys, M, verts, joints, p2f, ws)
@@ -414,7 +416,7 @@ class _RenderFunction(torch.autograd.Function):
                                         cube_size.data_ptr(), view.data_ptr(), xs.data_ptr(), ys.data_ptr(), M.data_ptr(),
                                         ctx.render._intr, verts.data_ptr(), joints.data_ptr(), p2f.data_ptr(),
                                         L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), L.ptr(gs[3]), g_prm.data_ptr(),
-                                        ws.data_ptr(), L.stream_ptr()))
+                                        ws.data_ptr(), ctx.render.raster_flags, L.stream_ptr()))
         return None, g_prm, None, None, None, None, None, None
 
 
@@ -472,10 +474,18 @@ class Render(nn.Module):
 
     ``mode='literal'`` reproduces the reference's 640x640 raster -> resize -> crop chain by
     rasterising only the raster pixel each crop pixel reads; ``mode='direct'`` rasterises the
-    crop directly with crop-space intrinsics (the benchmark configuration)."""
+    crop directly with crop-space intrinsics (the benchmark configuration).
 
-    def __init__(self, mano_path, dataset, cam_para, image_size, crop_size=(128, 128), mode="literal"):
+    ``perspective_correct`` is pytorch3d's RasterizationSettings flag.  The reference never passes it
+    (mano_layer.py:946-950) and pytorch3d 0.4.0 - the release it pins - defaults it to False (depth
+    interpolated with the screen-space barycentrics), so that is the default here; True reproduces what
+    later pytorch3d releases infer for perspective cameras."""
+
+    def __init__(self, mano_path, dataset, cam_para, image_size, crop_size=(128, 128), mode="literal",
+                 perspective_correct=False):
         super().__init__()
+        self.perspective_correct = bool(perspective_correct)
+        self.raster_flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
         if isinstance(mano_path, dict):
             self.mano_layer = MANO_SMPL(mano_path, dataset)
         else:
@@ -525,7 +535,7 @@ class Render(nn.Module):
 
     def _rasterize(self, hand_verts, center3d, cube_size, M=None):
         view, xs, ys, M_out = self._view(center3d, cube_size, M)
-        img, p2f = _RasterFunction.apply(self.mano_layer, hand_verts, view, xs, ys)
+        img, p2f = _RasterFunction.apply(self.mano_layer, hand_verts, view, xs, ys, self.raster_flags)
         return img, p2f, M_out
 
     @staticmethod

@@ -33,7 +33,22 @@ enum DsfStatus {
 #define DSF_NBETA 10
 #define DSF_NPOSE 135
 #define DSF_NSPHERE 66
-#define DSF_VIEW_STRIDE 16 /* floats per hand in a view record, see dsf_view_setup */
+#define DSF_VIEW_STRIDE 20 /* floats per hand in a view record, see dsf_view_setup */
+
+/* Rasteriser flags (the `flags` argument of the raster / render / fit entry points).
+ * DSF_RASTER_PERSPECTIVE_CORRECT = pytorch3d's RasterizationSettings.perspective_correct.  The reference
+ * builds RasterizationSettings(image_size, blur_radius=0, faces_per_pixel=1) without it
+ * (render_model/mano_layer.py:946-950); in the pytorch3d 0.4.0 it pins (README.md:41) that argument defaults to
+ * False and MeshRasterizer.forward passes it on unchanged, so flags = 0 - z interpolated with the screen-space
+ * barycentrics - is the reference's behaviour.  Later pytorch3d releases infer True for perspective cameras;
+ * the flag reproduces that. */
+#define DSF_RASTER_PERSPECTIVE_CORRECT 1
+/* DSF_RASTER_SEPARATE_BACKWARD: the fused steps run the raster backward as its own kernel even when the
+ * rasteriser's epilogue could emit the vertex gradient (flags without PERSPECTIVE_CORRECT).  The epilogue works
+ * with integer pixel moments and px = 1 - (2 q + 1) / S, which is exact when S is a power of two (the direct
+ * R x R raster); in the literal 640-pixel raster the float32 sample coordinates deviate from it by up to one
+ * ulp, which the per-pixel kernel sees and the moments do not - callers in literal mode set this flag. */
+#define DSF_RASTER_SEPARATE_BACKWARD 2
 
 const char* dsf_last_error_string(void);
 int dsf_version(void);
@@ -99,16 +114,18 @@ int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParams* p, float
  * mode 1 "literal": the S x S raster -> (H,W) resize -> crop chain, evaluated only at the
  *         raster pixel each crop pixel reads (S = max(W,H)); M_in (B,3,3) optional (M_render /
  *         getDepth pass their own, must be axis-aligned), else recomputed like render() does.
- * Outputs: view (B,16) = [fxn,fyn,pxn,pyn, zc,zhalf,bg, ax,bx,ay,by, x_lo,x_hi,y_lo,y_hi(as float), affine]
+ * Outputs: view (B,20) = [fxn,fyn,pxn,pyn, zc,zhalf,bg, ax,bx,ay,by, x_lo,x_hi,y_lo,y_hi(as float), affine,
+ *          S, 0,0,0]
  *          (affine = 1 when sample index = a * ndc + b holds exactly, i.e. mode 0; the rasteriser then
- *          converts run ends analytically instead of searching xs),
+ *          converts run ends analytically instead of searching xs; S = side of the square raster whose
+ *          pixels the samples are: R in mode 0, max(W,H) in mode 1),
  *          xs (B,R), ys (B,R) NDC sample coordinates (NaN = reads zero padding), M_out (B,3,3) or NULL. */
 int dsf_view_setup(int mode, int batch, const float* center3d, const float* cube,
                    const float* intr4, int W, int H, int R, const float* M_in, float* view,
                    float* xs, float* ys, float* M_out, dsfStream_t stream);
 
 /* R1/R4  replaces self.rasterizer(meshes) (mano_layer.py:1083, pytorch3d 0.4.0
- * _C.rasterize_meshes, faces_per_pixel=1, blur_radius=0, perspective-correct) fused with the
+ * _C.rasterize_meshes, faces_per_pixel=1, blur_radius=0, perspective_correct = flags & 1) fused with the
  * background fill (:1084-1085) and normalize_img (:1289-1299).
  * verts_cam (NM,779,3) camera-space mm; faces come from the handle.
  * img (NM,R,R) normalised depth; pix_to_face (NM,R,R) int32 (-1 bg, index local to the mesh);
@@ -118,7 +135,7 @@ int dsf_view_setup(int mode, int batch, const float* center3d, const float* cube
 int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                        const float* xs, const float* ys, int R, float* img, int* pix_to_face,
                        float* zbuf, float* bary, float* dists, const float* target, float thr,
-                       float* loss_parts_tile, dsfStream_t stream);
+                       float* loss_parts_tile, int flags, dsfStream_t stream);
 /* number of tiles per mesh = length of the per-mesh partial-sum records of loss_parts_tile */
 int dsf_raster_tiles(int R);
 
@@ -127,7 +144,23 @@ int dsf_raster_tiles(int R);
  * g_verts_cam (NM,779,3) overwritten. */
 int dsf_raster_backward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
                         const float* xs, const float* ys, int R, const int* pix_to_face,
-                        const float* g_img, float* g_verts_cam, dsfStream_t stream);
+                        const float* g_img, float* g_verts_cam, int flags, dsfStream_t stream);
+
+/* R1 + R4 + L2 + R2 in one rasteriser launch, for camera-space vertices from any source (flags must not
+ * contain DSF_RASTER_PERSPECTIVE_CORRECT): rasterise + normalise, the inline m2d loss against target (NM,R,R)
+ * (train_render.py:728-732: union mask at thr, per-mesh normalised, x loss_weight / norm_batch; norm_batch <= 0
+ * means n_mesh) and d loss / d verts_cam.  Without perspective correction the depth of a face is affine in the
+ * sample position, so the zbuf cotangent of a face reduces to three integer moments of sign(img - target) over
+ * its pixels; the epilogue accumulates them, evaluates one closed-form gradient per touched face and gathers per
+ * vertex - no pix_to_face plane, no second pass.  img (NM,R,R); pix_to_face (NM,R,R) or NULL (not written);
+ * parts (NM,2), totals (4) as dsf_depth_loss mode 0; g_verts_cam (NM,779,3) or NULL (then the per-tile shares
+ * stay in the workspace); workspace: dsf_raster_loss_workspace_floats(n_mesh, R) floats.  3 launches (raster,
+ * loss fold, gradient-share reduction). */
+long dsf_raster_loss_workspace_floats(int n_mesh, int R);
+int dsf_raster_loss_grad(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,
+                         const float* xs, const float* ys, int R, const float* target, float thr,
+                         float loss_weight, int norm_batch, float* img, int* pix_to_face, float* parts,
+                         float* totals, float* g_verts_cam, float* workspace, int flags, dsfStream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * L1/L2  render losses.
@@ -197,14 +230,25 @@ const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces);
  * gradients are scaled alike, and combines totals[3] (un-normalised loss) itself.
  * crop_joints (B,n,3) or NULL: teacher joints for crop_hand of the rendered image before the loss.
  * Outputs: img (B,R,R), pix_to_face (B,R,R), verts (B,779,3), joints (B,21,3) (normalised cube
- * units, global_scale 1/125), g_params (B,62) = d loss/d params, parts (B,2), totals (4). */
+ * units, global_scale 1/125), g_params (B,62) = d loss/d params, parts (B,2), totals (4).
+ * flags = 0 (the reference's rasteriser settings): depth is affine over a face, so the rasteriser's epilogue
+ * reduces the loss gradient to three integer moments per face and emits the vertex gradient itself - the step
+ * is 7 launches (pose, blend GEMM, skin | raster+loss+raster-backward | skin bwd, GEMM bwd, pose bwd; the loss
+ * records parts / totals ride along with the last three), the pix_to_face plane is not needed and pix_to_face
+ * may be NULL (not written).
+ * flags & DSF_RASTER_PERSPECTIVE_CORRECT: separate raster-backward kernel, pix_to_face required. */
 long dsf_fit_workspace_floats(int batch, int R);
 int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
                  const float* cube, const float* view, const float* xs, const float* ys,
                  const float* target, float loss_weight, int norm_batch, const float* crop_joints,
                  int n_crop_joints, const float* crop_M, const float* intr4, float* img, int* pix_to_face,
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
-                 float* workspace, dsfStream_t stream);
+                 float* workspace, int flags, dsfStream_t stream);
+
+/* totals (4) of one batch that ran as n_slices dsf_fit_step calls (slice_totals (n_slices,4), each with
+ * norm_batch = the full batch): sums [1],[2],[3] and sets [0] = sum [3] / norm_batch.  One tiny launch, so a
+ * sliced step stays free of framework ops inside a captured graph. */
+int dsf_sum_totals(int n_slices, const float* slice_totals, int norm_batch, float* totals, dsfStream_t stream);
 
 /* Multi-view fused step (BASELINE config "high-res multi-view"): MANO once per hand; per view v the posed
  * hand is rotated about center3d[b] by rot[b, v] (3x3 row-major; RotationPoints :874-885 as getDepth uses it,
@@ -217,7 +261,7 @@ int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R, const floa
                        const float* center3d, const float* cube, const float* rot, const float* view,
                        const float* xs, const float* ys, const float* target, float loss_weight,
                        float* img, int* pix_to_face, float* verts, float* joints, float* g_params,
-                       float* parts, float* totals, float* workspace, dsfStream_t stream);
+                       float* parts, float* totals, float* workspace, int flags, dsfStream_t stream);
 
 /* R5 - Render.render (render_model/mano_layer.py:1071-1097) as one forward and one backward call for the
  * autograd drop-in: params (B, ld_params >= 62 | 63) = [quat(3|4) | theta45 | beta10 | scale, trans3],
@@ -232,13 +276,13 @@ int dsf_render_forward(const DsfMano* h, int batch, int R, const float* params, 
                        const float* center3d, const float* cube, const float* view, const float* xs,
                        const float* ys, const float* M, const float* intr4, float* img, int* pix_to_face,
                        float* verts, float* joints, float* joint_uvd, float* joint_xyz, float* mesh_xyz,
-                       float* workspace, dsfStream_t stream);
+                       float* workspace, int flags, dsfStream_t stream);
 int dsf_render_backward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
                         const float* center3d, const float* cube, const float* view, const float* xs,
                         const float* ys, const float* M, const float* intr4, const float* verts,
                         const float* joints, const int* pix_to_face, const float* g_img,
                         const float* g_joint_uvd, const float* g_joint_xyz, const float* g_mesh_xyz,
-                        float* g_params, float* workspace, dsfStream_t stream);
+                        float* g_params, float* workspace, int flags, dsfStream_t stream);
 
 /* "next" row f1 - replaces loader.crop_hand (data/render_loader.py:1209-1227, with uvdImg2xyzImg
  * :1190-1200): pixels whose back-projected point falls outside the box around the teacher skeleton

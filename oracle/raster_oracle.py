@@ -21,6 +21,18 @@ from . import mano_oracle as mo
 _lib = None
 VIEW_STRIDE = 8   # fxn, fyn, pxn, pyn, zc, zhalf, bg, pad
 
+# RasterizationSettings.perspective_correct as the reference gets it: mano_layer.py:946-950 builds
+# RasterizationSettings(image_size, blur_radius=0.0, faces_per_pixel=1) and nothing else, and in
+# pytorch3d 0.4.0 (README.md:41) the constructor default is `perspective_correct: bool = False`, passed on
+# unchanged by MeshRasterizer.forward (the inference "True for perspective cameras" arrived in 0.5.0 together
+# with Optional[bool] = None).  Recalled, not vendored - so both settings stay testable; every function below
+# takes perspective_correct=None meaning this default.
+PERSPECTIVE_CORRECT = False
+
+
+def _pc(flag):
+    return PERSPECTIVE_CORRECT if flag is None else bool(flag)
+
 
 def lib():
     global _lib
@@ -88,7 +100,7 @@ def normalize_depth(zbuf, view):
     return mo.normalize_img(z[:, None], view[:, 4], view[:, 5] * 2)[:, 0]
 
 
-def render(verts, faces, view, xs, ys, perspective_correct=True, eps=1e-8, zcull_mode=0, want_bary=False):
+def render(verts, faces, view, xs, ys, perspective_correct=None, eps=1e-8, zcull_mode=0, want_bary=False):
     """verts (B,V,3) camera-space mm, faces (F,3) int32 -> pix_to_face (B,R,R) i32, zbuf, [bary], vndc."""
     verts = verts.detach().float().contiguous()
     faces = faces.int().contiguous()
@@ -100,12 +112,12 @@ def render(verts, faces, view, xs, ys, perspective_correct=True, eps=1e-8, zcull
     vndc = torch.empty(B, V, 3)
     lib().orc_batch_render_f32(
         _p(verts), B, V, _p(faces, ctypes.c_int), faces.shape[0], _p(view), _p(xs), _p(ys), R,
-        int(perspective_correct), ctypes.c_float(eps), zcull_mode, _p(p2f, ctypes.c_int), _p(zbuf),
+        int(_pc(perspective_correct)), ctypes.c_float(eps), zcull_mode, _p(p2f, ctypes.c_int), _p(zbuf),
         _p(bary), _p(vndc))
     return p2f, zbuf, bary, vndc
 
 
-def render_f64(verts, faces, view, xs, ys, perspective_correct=True, eps=1e-8, zcull_mode=0):
+def render_f64(verts, faces, view, xs, ys, perspective_correct=None, eps=1e-8, zcull_mode=0):
     """Same rasteriser evaluated in float64 from the same float32 inputs: pixels where it
     disagrees with the float32 build are rounding-ambiguous (tie class T2)."""
     L = lib()
@@ -122,12 +134,12 @@ def render_f64(verts, faces, view, xs, ys, perspective_correct=True, eps=1e-8, z
                           ctypes.c_float(view[b, 2]), ctypes.c_float(view[b, 3]), _p(vn, ctypes.c_double))
         L.orc_rasterize_f64(_p(vn, ctypes.c_double), _p(faces, ctypes.c_int), faces.shape[0],
                             _p(xs64[b], ctypes.c_double), R, _p(ys64[b], ctypes.c_double), R,
-                            int(perspective_correct), ctypes.c_double(eps), zcull_mode,
+                            int(_pc(perspective_correct)), ctypes.c_double(eps), zcull_mode,
                             _p(p2f[b], ctypes.c_int), _p(zbuf[b], ctypes.c_double), None, None)
     return p2f, zbuf
 
 
-def render_backward(verts, faces, view, xs, ys, p2f, grad_zbuf, vndc, perspective_correct=True, eps=1e-8):
+def render_backward(verts, faces, view, xs, ys, p2f, grad_zbuf, vndc, perspective_correct=None, eps=1e-8):
     verts = verts.detach().float().contiguous()
     faces = faces.int().contiguous()
     B, V, _ = verts.shape
@@ -136,18 +148,55 @@ def render_backward(verts, faces, view, xs, ys, p2f, grad_zbuf, vndc, perspectiv
     scratch = torch.empty(B, V, 3)
     lib().orc_batch_render_backward_f32(
         _p(verts), B, V, _p(faces, ctypes.c_int), _p(view), _p(xs), _p(ys), R, _p(p2f, ctypes.c_int),
-        _p(grad_zbuf.float().contiguous()), int(perspective_correct), ctypes.c_float(eps), _p(vndc),
+        _p(grad_zbuf.float().contiguous()), int(_pc(perspective_correct)), ctypes.c_float(eps), _p(vndc),
         _p(scratch), _p(gv))
     return gv
 
 
+def render_backward_f64(verts, faces, view, xs, ys, p2f, grad_zbuf, perspective_correct=None, eps=1e-8, vndc=None):
+    """The same backward evaluated in float64 - the yardstick for gradient tolerances: the float32 per-pixel
+    chain rule (pytorch3d's and its restatement alike) loses up to ~1e-3 to cancellation on sliver faces, more
+    in the literal 640-pixel raster where float32 NDC coordinates resolve only 2e-5 of a pixel.  With vndc (the
+    float32 projected vertices the forward really used, as returned by render()) the gradient is taken at exactly
+    the point the forward evaluated; without it the vertices are projected in float64.
+    -> grad wrt the camera-space vertices (B,V,3) float64."""
+    L = lib()
+    verts = verts.detach().float().contiguous()
+    faces = faces.int().contiguous()
+    B, V, _ = verts.shape
+    R = xs.shape[1]
+    cd, ci, cf = ctypes.c_double, ctypes.c_int, ctypes.c_float
+    out = torch.zeros(B, V, 3, dtype=torch.float64)
+    xs64, ys64 = xs.double().contiguous(), ys.double().contiguous()
+    gz = grad_zbuf.double().contiguous()
+    p2f = p2f.int().contiguous()
+    for b in range(B):
+        v4 = [cf(float(view[b, i])) for i in range(4)]
+        if vndc is None:
+            vn = torch.empty(V, 3, dtype=torch.float64)
+            L.orc_project_f64(_p(verts[b]), V, *v4, _p(vn, cd))
+        else:
+            vn = vndc[b].double().contiguous()
+        gvn = torch.zeros(V, 3, dtype=torch.float64)
+        L.orc_rasterize_backward_f64(_p(vn, cd), _p(faces, ci), _p(xs64[b], cd), R, _p(ys64[b], cd), R,
+                                     _p(p2f[b], ci), _p(gz[b], cd), None, int(_pc(perspective_correct)), cd(eps),
+                                     _p(gvn, cd))
+        L.orc_project_backward_f64(_p(verts[b]), V, *v4, _p(gvn, cd), _p(out[b], cd))
+    return out
+
+
 class RasterDepth(torch.autograd.Function):
     """verts (B,V,3) -> raw zbuf (B,R,R) with -1 background; gradient as pytorch3d's
-    rasterize_meshes_backward feeds it (zbuf only, mano_layer.py:1084)."""
+    rasterize_meshes_backward feeds it (zbuf only, mano_layer.py:1084).  The forward is the float32
+    restatement (bit-level yardstick); the backward is evaluated in float64 at the float32 forward's own
+    projected vertices (render_backward_f64), because the float32 per-pixel chain rule carries up to ~1e-3 of
+    cancellation noise - more than the 1e-4 the parity tests ask for.  render_backward() keeps the float32
+    restatement; tests/test_raster_oracle_cpu.py bounds its distance from this one."""
 
     @staticmethod
-    def forward(ctx, verts, faces, view, xs, ys):
-        p2f, zbuf, _, vndc = render(verts, faces, view, xs, ys)
+    def forward(ctx, verts, faces, view, xs, ys, perspective_correct=None):
+        p2f, zbuf, _, vndc = render(verts, faces, view, xs, ys, perspective_correct)
+        ctx.pc = perspective_correct
         ctx.save_for_backward(verts, faces, view, xs, ys, p2f, vndc)
         ctx.mark_non_differentiable(p2f)
         return zbuf, p2f
@@ -155,7 +204,8 @@ class RasterDepth(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_zbuf, _g):
         verts, faces, view, xs, ys, p2f, vndc = ctx.saved_tensors
-        return render_backward(verts, faces, view, xs, ys, p2f, g_zbuf, vndc), None, None, None, None
+        g = render_backward_f64(verts, faces, view, xs, ys, p2f, g_zbuf, ctx.pc, vndc=vndc)
+        return g.to(verts.dtype), None, None, None, None, None
 
 
 def point_face(points, verts, faces, eps=1e-8):

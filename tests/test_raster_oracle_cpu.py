@@ -3,6 +3,7 @@ reference, so: known answers, float64 cross-evaluation, finite differences, brut
 import ctypes
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import mano_oracle as mo
@@ -54,19 +55,21 @@ def test_lowest_face_index_wins_exact_ties():
     assert set(p2f.unique().tolist()) == {-1, 0}
 
 
-def test_f32_and_f64_rasterisers_agree_except_rounding_ties(mano_model):
+@pytest.mark.parametrize("pc", [False, True])
+def test_f32_and_f64_rasterisers_agree_except_rounding_ties(mano_model, pc):
     c, inp, vw = _scene(mano_model, 4, 3)
     for mode in ("direct", "literal"):
         view, xs, ys, _ = ro.make_view(mode, inp["center3d"], inp["cube"], NYU, 640, 480, 128)
-        p32, z32, _, _ = ro.render(vw, c.faces, view, xs, ys)
-        p64, z64 = ro.render_f64(vw, c.faces, view, xs, ys)
+        p32, z32, _, _ = ro.render(vw, c.faces, view, xs, ys, perspective_correct=pc)
+        p64, z64 = ro.render_f64(vw, c.faces, view, xs, ys, perspective_correct=pc)
         assert (p32 >= 0).float().mean() > 0.05
         assert (p32 != p64).float().mean() < 1e-3
         same = (p32 == p64) & (p32 >= 0)
         assert ((z32[same].double() - z64[same]).abs() / z64[same]).max() < 1e-5
 
 
-def test_raster_backward_matches_finite_differences(mano_model):
+@pytest.mark.parametrize("pc", [0, 1])
+def test_raster_backward_matches_finite_differences(mano_model, pc):
     c, inp, vw = _scene(mano_model, 1, 5)
     view, xs, ys, _ = ro.make_view("direct", inp["center3d"], inp["cube"], NYU, 640, 480, 128)
     L = ro.lib()
@@ -83,7 +86,7 @@ def test_raster_backward_matches_finite_differences(mano_model):
         p = torch.empty(R, R, dtype=torch.int32)
         z = torch.empty(R, R, dtype=torch.float64)
         L.orc_rasterize_f64(ro._p(vn, cd), ro._p(faces, ci), faces.shape[0], ro._p(xs64, cd), R, ro._p(ys64, cd),
-                            R, 1, cd(1e-8), 0, ro._p(p, ci), ro._p(z, cd), None, None)
+                            R, pc, cd(1e-8), 0, ro._p(p, ci), ro._p(z, cd), None, None)
         return vn, p, z
 
     base = vw[0].contiguous()
@@ -91,7 +94,7 @@ def test_raster_backward_matches_finite_differences(mano_model):
     gz = torch.randn(R, R, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
     gvn = torch.zeros(V, 3, dtype=torch.float64)
     L.orc_rasterize_backward_f64(ro._p(vn, cd), ro._p(faces, ci), ro._p(xs64, cd), R, ro._p(ys64, cd), R,
-                                 ro._p(p0, ci), ro._p(gz, cd), None, 1, cd(1e-8), ro._p(gvn, cd))
+                                 ro._p(p0, ci), ro._p(gz, cd), None, pc, cd(1e-8), ro._p(gvn, cd))
     gv = torch.zeros(V, 3, dtype=torch.float64)
     L.orc_project_backward_f64(ro._p(base), V, *v4, ro._p(gvn, cd), ro._p(gv, cd))
     # finite differences on a few vertices that own foreground pixels (visibility held fixed by
@@ -111,13 +114,13 @@ def test_raster_backward_matches_finite_differences(mano_model):
             gvn2 = torch.zeros(V, 3, dtype=torch.float64)
             pk = torch.where(keep, p0, torch.full_like(p0, -1)).contiguous()
             L.orc_rasterize_backward_f64(ro._p(vn, cd), ro._p(faces, ci), ro._p(xs64, cd), R, ro._p(ys64, cd), R,
-                                         ro._p(pk, ci), ro._p(gz, cd), None, 1, cd(1e-8), ro._p(gvn2, cd))
+                                         ro._p(pk, ci), ro._p(gz, cd), None, pc, cd(1e-8), ro._p(gvn2, cd))
             gv2 = torch.zeros(V, 3, dtype=torch.float64)
             L.orc_project_backward_f64(ro._p(base), V, *v4, ro._p(gvn2, cd), ro._p(gv2, cd))
             assert abs(fd - gv2[v, ax]) <= 2e-5 * max(1.0, abs(gv2[v, ax])), (v, ax, fd, gv2[v, ax])
     # float32 backward agrees with the float64 one
-    p32, z32, _, vndc = ro.render(vw, c.faces, view, xs, ys)
-    g32 = ro.render_backward(vw, c.faces, view, xs, ys, p32, gz.float()[None], vndc)
+    p32, z32, _, vndc = ro.render(vw, c.faces, view, xs, ys, perspective_correct=bool(pc))
+    g32 = ro.render_backward(vw, c.faces, view, xs, ys, p32, gz.float()[None], vndc, perspective_correct=bool(pc))
     if torch.equal(p32[0], p0):
         assert (g32[0].double() - gv).abs().max() <= 2e-4 * gv.abs().max()
 
