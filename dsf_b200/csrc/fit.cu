@@ -121,7 +121,7 @@ extern "C" int dsf_raster_loss_grad(const DsfMano* h, int n_mesh, const float* v
     int* gv_flag = reinterpret_cast<int*>(parts_tile + (size_t)n_mesh * n_tiles * 2);
     float* gv_tile = reinterpret_cast<float*>(gv_flag + (size_t)n_mesh * n_tiles);
     RasterFused rf = {gv_tile, gv_flag};
-    if (flags & 256) rf.gv_tile = nullptr;          // tuning aid: forward + loss sums only
+    if (flags & 4096) rf.gv_tile = nullptr;         // tuning aid: forward + loss sums only
     int rc = dsf_raster_forward_impl(h, n_mesh, verts_cam, nullptr, nullptr, view, xs, ys, R, img, pix_to_face, nullptr,
                                      nullptr, nullptr, target, thr, parts_tile, nullptr, flags & 3, &rf, st);
     if (rc) return rc;

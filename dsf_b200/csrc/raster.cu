@@ -188,9 +188,10 @@ __device__ __forceinline__ void project_vertex(const float* v, const float* plac
                                                const ViewRec& vw, float* out) {
     float x = v[0], y = v[1], z = v[2];
     if (place_scale) {
-        x = __fadd_rn(__fdiv_rn(__fmul_rn(x, place_scale[0]), 2.f), place_off[0]);
-        y = __fadd_rn(__fdiv_rn(__fmul_rn(y, place_scale[1]), 2.f), place_off[1]);
-        z = __fadd_rn(__fdiv_rn(__fmul_rn(z, place_scale[2]), 2.f), place_off[2]);
+        // (v * cube) / 2 + centre; the division by two is exact, written as a multiplication
+        x = __fadd_rn(__fmul_rn(__fmul_rn(x, place_scale[0]), 0.5f), place_off[0]);
+        y = __fadd_rn(__fmul_rn(__fmul_rn(y, place_scale[1]), 0.5f), place_off[1]);
+        z = __fadd_rn(__fmul_rn(__fmul_rn(z, place_scale[2]), 0.5f), place_off[2]);
     }
     out[0] = __fdiv_rn(__fadd_rn(__fmul_rn(vw.fxn, -x), __fmul_rn(vw.pxn, z)), z);
     out[1] = __fdiv_rn(__fadd_rn(__fmul_rn(vw.fyn, -y), __fmul_rn(vw.pyn, z)), z);
@@ -730,29 +731,34 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     float* red = reinterpret_cast<float*>(scratch + 32);                            // 32 .. 95
     int* qx = reinterpret_cast<int*>(scratch + 96);                                 // raster column of each tile column, minus q0x
     int* qy = qx + RT_TW;                                                           // ... rows
-    unsigned long long* mom = reinterpret_cast<unsigned long long*>(scratch + 320); // (F) packed face moments
+    int* s_gmax = reinterpret_cast<int*>(scratch + 288);                            // float bits of max |face gradient| (xy, z)
+    int* mom = reinterpret_cast<int*>(scratch + 320);                               // (F,3) face moments: sum s, sum s dqx, sum s dqy
     const int Fp = (F + 31) & ~31;
-    unsigned short* flist = reinterpret_cast<unsigned short*>(mom + Fp);            // per-warp lists of touched faces
-    float* sgn = reinterpret_cast<float*>(flist + Fp);                              // (NVW,3) NDC vertex gradients
+    unsigned short* flist = reinterpret_cast<unsigned short*>(mom + 3 * Fp);        // per-warp lists of touched faces (after the
+                                                                                    // pixel loop; before, its group lists)
+    int* sgn = reinterpret_cast<int*>(flist + Fp);                                  // (NVW,3) NDC vertex gradients, fixed point
     const bool do_crop = target && crop.joints;
     // Fused backward (no perspective correction): the depth of a face is affine in the sample position,
     // pz(p) = [z0 e0(p) + z1 e1(p) + z2 e2(p)] / area, so the whole zbuf cotangent of a face collapses to the
     // three moments (sum g, sum g px, sum g py) over its pixels, and d loss / d img of the m2d loss is
     // +-gk(hand) on the union mask.  The epilogue accumulates integer moments of sign(synth - real) per face -
-    // px = 1 - (2 q + 1) / S with the integer raster pixel q - packed into one 64-bit word (n << 48 |
-    // sum s dqy << 24 | sum s dqx, signed fields relative to the tile's first sample) and added with one native
-    // shared-memory atomic per run of equal faces; each warp then compacts its share of the face list to the
-    // touched faces, evaluates their closed-form gradient and scatters it to the vertices, and the vertices are
-    // chained through the projection.  The per-hand factor gk / zhalf is applied by the consumer (it needs the
-    // mask count of all tiles).  No pix_to_face plane, no second pass over target / img, no backward kernel.
+    // px = 1 - (2 q + 1) / S with the integer raster pixel q, relative to the tile's first sample - with native
+    // 32-bit shared-memory atomics (64-bit and float adds are compare-and-swap loops on this architecture, measured
+    // 2x slower here); each warp then compacts its share of the face list to the touched faces and evaluates their
+    // closed-form gradient (float64); the face gradients are scattered to the vertices in fixed point (scale = a
+    // power of two from the tile's largest entry, again native integer atomics: exact, order-independent sums), and
+    // the vertices are chained through the projection.  The per-hand factor gk / zhalf is applied by the consumer
+    // (it needs the mask count of all tiles).  No pix_to_face plane, no second pass over target / img, no backward
+    // kernel, bit-reproducible.
     const bool do_grad = !PERSP && tail.gv_tile != nullptr && target != nullptr;
     if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
     const float cx0s = s.xs[tx0], cy0s = s.ys[ty0];
     const int q0x = (cx0s == cx0s) ? __float2int_rn(((1.f - cx0s) * vw.S - 1.f) * 0.5f) : 0;
     const int q0y = (cy0s == cy0s) ? __float2int_rn(((1.f - cy0s) * vw.S - 1.f) * 0.5f) : 0;
     if (do_grad) {
-        for (int i = tid; i < Fp; i += RT_THREADS) mom[i] = 0ull;
-        for (int i = tid; i < NVW * 3; i += RT_THREADS) sgn[i] = 0.f;
+        for (int i = tid; i < 3 * Fp; i += RT_THREADS) mom[i] = 0;
+        for (int i = tid; i < NVW * 3; i += RT_THREADS) sgn[i] = 0;
+        if (tid < 2) s_gmax[tid] = 0;
         for (int i = tid; i < tw + th; i += RT_THREADS) {
             const bool isx = i < tw;
             const float c = isx ? s.xs[tx0 + i] : s.ys[ty0 + i - tw];
@@ -763,78 +769,113 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     if (do_crop || do_grad) __syncthreads();
     auto add_moments = [&](int f, int n, int mi, int dqy) {
         if (f >= 0 && (n | mi) != 0) {
-            const long long v = ((long long)n << 48) + ((long long)(n * dqy) << 24) + (long long)mi;
-            atomicAdd(&mom[f], (unsigned long long)v);
+            if (n) { atomicAdd(&mom[3 * f], n); atomicAdd(&mom[3 * f + 2], n * dqy); }
+            if (mi) atomicAdd(&mom[3 * f + 1], mi);
         }
     };
     const bool fast = !zbuf && !bary && !dists && (R & 3) == 0 && (tw & 3) == 0;
     if (fast) {
-        // default outputs only: four pixels per lane, 128-bit key / target loads and image stores;
-        // background pixels (most of the image) take the precomputed normalised far plane
+        // default outputs only: four pixels per lane, 128-bit key / target loads and image stores.  Two passes
+        // per warp over its own rows: (1) groups of four background pixels (most of the image) take the
+        // precomputed normalised far plane on the spot, every other group is pushed on a warp-private list;
+        // (2) the list is processed with all lanes busy (a row through the hand has ~1/3 of its groups on the hand).
         const float bgval = __fdiv_rn(__fsub_rn(zmax, vw.zc), vw.zh);
         const int qw = tw >> 2;
-        for (int ly = tid >> 5; ly < th; ly += RT_THREADS / 32) {
-            for (int q4 = lane; q4 < qw; q4 += 32) {
+        // general group: depth normalisation, loss terms, moments of the loss gradient
+        auto process_group = [&](int ly, int lx, const float4& tg, const ulonglong2& k01, const ulonglong2& k23) {
+            const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
+            const unsigned long long kk[4] = {k01.x, k01.y, k23.x, k23.y};
+            const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
+            float v[4];
+            int ff[4];
+            int run_f = -1, run_n = 0, run_mi = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bool grad_ok = false;                 // gates of the depth normalisation: bg fill and clamp pass no gradient
+                if (kk[c] == ~0ull) {
+                    v[c] = bgval;
+                    ff[c] = -1;
+                } else {
+                    const float z = __uint_as_float((unsigned int)(kk[c] >> 32));
+                    float d = z <= 0.f ? 0.f : z;
+                    d = (d == 0.f) ? zmax : d;
+                    d = d > zmax ? zmax : d;
+                    d = d < zmin_c ? zmin_c : d;
+                    v[c] = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
+                    ff[c] = (int)(unsigned int)(kk[c] & 0xffffffffu);
+                    grad_ok = z > 0.f && !(z > zmax) && !(z < zmin_c);
+                }
+                if (target) {
+                    const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh));
+                    const float vc = kept ? v[c] : 1.f;
+                    const bool m = tt[c] < thr || vc < thr;
+                    if (m) { l_sum += fabsf(tt[c] - vc); l_cnt += 1.f; }
+                    if (do_grad && grad_ok && kept && m) {
+                        const float d = vc - tt[c];
+                        const int sg = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
+                        if (sg) {
+                            if (ff[c] != run_f) {
+                                add_moments(run_f, run_n, run_mi, qy[ly]);
+                                run_f = ff[c]; run_n = 0; run_mi = 0;
+                            }
+                            run_n += sg;
+                            run_mi += sg * qx[lx + c];
+                        }
+                    }
+                }
+            }
+            if (do_grad) add_moments(run_f, run_n, run_mi, qy[ly]);
+            *reinterpret_cast<float4*>(img + o) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p2f) *reinterpret_cast<int4*>(p2f + o) = make_int4(ff[0], ff[1], ff[2], ff[3]);
+        };
+        // the list needs <= 128 groups per warp (64 x 128 tile: 4 rows x 32 groups) and room behind the tables
+        unsigned char* glist = reinterpret_cast<unsigned char*>(flist) + warp * 128;     // flist is not in use yet
+        const bool use_list = qw <= 32 && th <= 4 * (RT_THREADS / 32) && Fp * 2 >= (RT_THREADS / 32) * 128;
+        int n_list = 0;
+        for (int ly = warp, r = 0; ly < th; ly += RT_THREADS / 32, ++r) {
+            for (int q4 = lane; q4 < ((qw + 31) & ~31); q4 += 32) {
+                const bool in = q4 < qw;
                 const int lx = q4 * 4;
                 const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
                 float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (target) tg = __ldg(reinterpret_cast<const float4*>(target + o));
-                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
-                const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
-                const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
-                if ((k01.x & k01.y & k23.x & k23.y) == ~0ull && !do_crop) {
-                    // four background pixels (the common case): far plane out, loss only where the target has depth
+                ulonglong2 k01 = make_ulonglong2(~0ull, ~0ull), k23 = k01;
+                if (in) {
+                    if (target) tg = __ldg(reinterpret_cast<const float4*>(target + o));
+                    k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
+                    k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
+                }
+                const bool all_bg = (k01.x & k01.y & k23.x & k23.y) == ~0ull && !do_crop;
+                if (in && all_bg) {
+                    // four background pixels: far plane out, loss only where the target has depth
                     if (target) {
+                        const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if (tt[c] < thr || bgval < thr) { l_sum += fabsf(tt[c] - bgval); l_cnt += 1.f; }
                     }
                     *reinterpret_cast<float4*>(img + o) = make_float4(bgval, bgval, bgval, bgval);
                     if (p2f) *reinterpret_cast<int4*>(p2f + o) = make_int4(-1, -1, -1, -1);
-                    continue;
                 }
-                const unsigned long long kk[4] = {k01.x, k01.y, k23.x, k23.y};
-                float v[4];
-                int ff[4];
-                int run_f = -1, run_n = 0, run_mi = 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    bool grad_ok = false;                 // gates of the depth normalisation: bg fill and clamp pass no gradient
-                    if (kk[c] == ~0ull) {
-                        v[c] = bgval;
-                        ff[c] = -1;
-                    } else {
-                        const float z = __uint_as_float((unsigned int)(kk[c] >> 32));
-                        float d = z <= 0.f ? 0.f : z;
-                        d = (d == 0.f) ? zmax : d;
-                        d = d > zmax ? zmax : d;
-                        d = d < zmin_c ? zmin_c : d;
-                        v[c] = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
-                        ff[c] = (int)(unsigned int)(kk[c] & 0xffffffffu);
-                        grad_ok = z > 0.f && !(z > zmax) && !(z < zmin_c);
-                    }
-                    if (target) {
-                        const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh));
-                        const float vc = kept ? v[c] : 1.f;
-                        const bool m = tt[c] < thr || vc < thr;
-                        if (m) { l_sum += fabsf(tt[c] - vc); l_cnt += 1.f; }
-                        if (do_grad && grad_ok && kept && m) {
-                            const float d = vc - tt[c];
-                            const int sg = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
-                            if (sg) {
-                                if (ff[c] != run_f) {
-                                    add_moments(run_f, run_n, run_mi, qy[ly]);
-                                    run_f = ff[c]; run_n = 0; run_mi = 0;
-                                }
-                                run_n += sg;
-                                run_mi += sg * qx[lx + c];
-                            }
-                        }
-                    }
+                const bool general = in && !all_bg;
+                if (use_list) {
+                    const unsigned int mk = __ballot_sync(0xffffffffu, general);
+                    if (general) glist[n_list + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)((r << 5) | q4);
+                    n_list += __popc(mk);
+                } else if (general) {
+                    process_group(ly, lx, tg, k01, k23);
                 }
-                if (do_grad) add_moments(run_f, run_n, run_mi, qy[ly]);
-                *reinterpret_cast<float4*>(img + o) = make_float4(v[0], v[1], v[2], v[3]);
-                if (p2f) *reinterpret_cast<int4*>(p2f + o) = make_int4(ff[0], ff[1], ff[2], ff[3]);
+            }
+        }
+        if (use_list) {
+            __syncwarp();
+            for (int k = lane; k < n_list; k += 32) {
+                const int e = glist[k];
+                const int ly = warp + (e >> 5) * (RT_THREADS / 32), lx = (e & 31) * 4;
+                float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (target) tg = __ldg(reinterpret_cast<const float4*>(target + ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx)));
+                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
+                const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
+                process_group(ly, lx, tg, k01, k23);
             }
         }
     } else
@@ -901,30 +942,27 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         }
     }
     if (do_grad) {
-        __syncthreads();                                      // moments complete
+        __syncthreads();                                      // moments complete, z-buffer keys dead
         // each warp owns a contiguous share of the faces: compact it to the touched ones (ballot, no atomics),
         // then one lane per touched face
         const int share = (F + RT_THREADS / 32 - 1) / (RT_THREADS / 32);
         const int f_lo = warp * share, f_hi = min(F, f_lo + share);
         unsigned short* wl = flist + f_lo;
+        float* stg = reinterpret_cast<float*>(s.key) + (size_t)f_lo * 9;     // this warp's face gradients (key storage)
         int cnt = 0;
         for (int f0 = f_lo; f0 < f_hi; f0 += 32) {
             const int f = f0 + lane;
-            const bool act = f < f_hi && mom[f] != 0ull;
+            const bool act = f < f_hi && (mom[3 * f] | mom[3 * f + 1] | mom[3 * f + 2]) != 0;
             const unsigned int mk = __ballot_sync(0xffffffffu, act);
             if (act) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)f;
             cnt += __popc(mk);
         }
         __syncwarp();
+        float gmax_xy = 0.f, gmax_z = 0.f;
         for (int k = lane; k < cnt; k += 32) {
             const int f = wl[k];
-            // unpack the signed fields (low to high)
-            const long long pk64 = (long long)mom[f];
-            const int mi_r = (int)((pk64 << 40) >> 40);
-            const long long r1 = (pk64 - mi_r) >> 24;
-            const int mj_r = (int)((r1 << 40) >> 40);
-            const int n = (int)((r1 - mj_r) >> 24);
-            const int mi = mi_r + q0x * n, mj = mj_r + q0y * n;
+            const int n = mom[3 * f];
+            const int mi = mom[3 * f + 1] + q0x * n, mj = mom[3 * f + 2] + q0y * n;
             const unsigned int pk = s.fp[f];
             const int i0 = pk & 1023, i1 = (pk >> 10) & 1023, i2 = pk >> 20;
             // float64 for the handful of operations per touched face: sliver faces amplify rounding by
@@ -938,19 +976,50 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const double Uy = S0 * (1.0 - inv_S - y0) - 2.0 * inv_S * (double)mj;
             double g[9];
             face_grad<double>(z0, ax, ay, dz1, bx, by, dz2, S0, Ux, Uy, g);
-            atomicAdd(&sgn[3 * i0], (float)g[0]); atomicAdd(&sgn[3 * i0 + 1], (float)g[1]); atomicAdd(&sgn[3 * i0 + 2], (float)g[2]);
-            atomicAdd(&sgn[3 * i1], (float)g[3]); atomicAdd(&sgn[3 * i1 + 1], (float)g[4]); atomicAdd(&sgn[3 * i1 + 2], (float)g[5]);
-            atomicAdd(&sgn[3 * i2], (float)g[6]); atomicAdd(&sgn[3 * i2 + 1], (float)g[7]); atomicAdd(&sgn[3 * i2 + 2], (float)g[8]);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const float gf = (float)g[e];
+                stg[k * 9 + e] = gf;
+                if (e % 3 == 2) gmax_z = fmaxf(gmax_z, fabsf(gf)); else gmax_xy = fmaxf(gmax_xy, fabsf(gf));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gmax_xy = fmaxf(gmax_xy, __shfl_xor_sync(0xffffffffu, gmax_xy, o));
+            gmax_z = fmaxf(gmax_z, __shfl_xor_sync(0xffffffffu, gmax_z, o));
+        }
+        if (lane == 0 && cnt > 0) {       // non-negative floats order like their bit patterns
+            atomicMax(&s_gmax[0], __float_as_int(gmax_xy));
+            atomicMax(&s_gmax[1], __float_as_int(gmax_z));
         }
         const int tile_has = __syncthreads_or(cnt > 0 ? 1 : 0);
         const size_t slot = (size_t)mesh * gridDim.x + tile;
         if (tid == 0) tail.gv_flag[slot] = tile_has;
         if (tile_has) {
+            // fixed point: the largest entry maps to [2^26, 2^27), which leaves room for 16 incident faces per vertex
+            const float m_xy = __int_as_float(s_gmax[0]), m_z = __int_as_float(s_gmax[1]);
+            int e_xy = 0, e_z = 0;
+            frexpf(m_xy, &e_xy);
+            frexpf(m_z, &e_z);
+            const float q_xy = m_xy > 0.f && m_xy < INFINITY ? ldexpf(1.f, 27 - e_xy) : 0.f;
+            const float q_z = m_z > 0.f && m_z < INFINITY ? ldexpf(1.f, 27 - e_z) : 0.f;
+            for (int k = lane; k < cnt; k += 32) {
+                const unsigned int pk = s.fp[wl[k]];
+                const int iv[3] = {(int)(pk & 1023), (int)((pk >> 10) & 1023), (int)(pk >> 20)};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    atomicAdd(&sgn[3 * iv[c]], __float2int_rn(stg[k * 9 + 3 * c] * q_xy));
+                    atomicAdd(&sgn[3 * iv[c] + 1], __float2int_rn(stg[k * 9 + 3 * c + 1] * q_xy));
+                    atomicAdd(&sgn[3 * iv[c] + 2], __float2int_rn(stg[k * 9 + 3 * c + 2] * q_z));
+                }
+            }
+            __syncthreads();
+            const float r_xy = q_xy > 0.f ? 1.f / q_xy : 0.f, r_z = q_z > 0.f ? 1.f / q_z : 0.f;
             float* go = tail.gv_tile + slot * NVW * 3;
             float sxp = 1.f, syp = 1.f, szp = 1.f;
             if (ps) { sxp = ps[0] * 0.5f; syp = ps[1] * 0.5f; szp = ps[2] * 0.5f; }
             for (int v = tid; v < NVW; v += RT_THREADS) {
-                const float gxn = sgn[3 * v], gyn = sgn[3 * v + 1], gzn = sgn[3 * v + 2];
+                const float gxn = (float)sgn[3 * v] * r_xy, gyn = (float)sgn[3 * v + 1] * r_xy, gzn = (float)sgn[3 * v + 2] * r_z;
                 // x_ndc = -fxn x / z + pxn (same for y), z_ndc = z; fxn x / z = pxn - x_ndc
                 const float xn = s.vn[3 * v], yn = s.vn[3 * v + 1], iz = 1.f / s.vn[3 * v + 2];
                 go[3 * v] = -gxn * vw.fxn * iz * sxp;
@@ -1016,10 +1085,12 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
 }
 
 // can the forward epilogue produce the vertex gradient itself (see raster_fwd_kernel)?  Needs the affine depth of
-// the non-perspective-correct rasteriser (the scratch tables fit the candidate-list storage for any F <= RT_MAXF).
+// the non-perspective-correct rasteriser, and its per-face / per-vertex tables must fit the candidate-list storage
+// (true for the MANO mesh: 1554 faces).
 bool dsf_raster_fused_grad_ok(const DsfMano* h, int flags) {
-    (void)h;
-    return !(flags & (DSF_RASTER_PERSPECTIVE_CORRECT | DSF_RASTER_SEPARATE_BACKWARD));
+    const int Fp = (h->n_faces + 31) & ~31;
+    return !(flags & (DSF_RASTER_PERSPECTIVE_CORRECT | DSF_RASTER_SEPARATE_BACKWARD)) &&
+           320 + 3 * Fp + Fp / 2 + NVW * 3 <= (RT_THREADS / 32) * RT_WCANDS;
 }
 
 extern "C" int dsf_raster_forward(const DsfMano* h, int n_mesh, const float* verts_cam, const float* view,

@@ -42,6 +42,5 @@ def t(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 for name, fn in [("plain fwd (img+p2f)", plain(False, True)), ("fwd + target/loss parts (+p2f)", plain(True, True)),
-                 ("fused: no grad, no totals", fused(256 | 512)), ("fused: no grad", fused(256)),
-                 ("fused: no totals", fused(512)), ("fused: full", fused(0))]:
+                 ("fused: no grad", fused(4096)), ("fused: full", fused(0))]:
     print(f"{name:36s} {t(fn):.4f} ms")
