@@ -94,6 +94,10 @@ SIGNATURES = {
     "dsf_intersect_vox": (_I, [_I, _I, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_rotate_points": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP]),
     "dsf_rotate_points_backward": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_mask_img": (_I, [_I, _I, _VP, _I, _VP, _VP, _VP, _VP]),
+    "dsf_synth2real": (_I, [_I, _I, _VP, _VP, _I, _F, _F, _VP, _VP]),
+    "dsf_chamfer_forward": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_chamfer_backward": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_uvd_img_to_xyz": (_I, [_I, _I, _VP, _VP, _VP, _VP, c_float_p, _F, _F, _VP, _VP, _VP]),
 }
 

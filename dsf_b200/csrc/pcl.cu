@@ -264,10 +264,12 @@ extern "C" int dsf_img2pcl(int batch, int R_in, int feature_size, const float* i
     const float4 in4 = make_float4(intr4[0], intr4[1], intr4[2], intr4[3]);
     if (feature_size <= 128) {
         const size_t smem = (size_t)feature_size * feature_size * sizeof(unsigned int);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[16] = {};          // the attribute is per device
+        int dev = 0;
+        DSF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 16 || !attr_set[dev]) {
             DSF_CHECK_CUDA(cudaFuncSetAttribute(img2pcl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
-            attr_set = true;
+            if (dev < 16) attr_set[dev] = true;
         }
         img2pcl_kernel<true><<<batch, PCL_THREADS, smem, (cudaStream_t)stream>>>(
             R_in, feature_size, img, center3d, cube, M, in4, img_size, flip, sample_num, seed, out_rows, pcl, count);

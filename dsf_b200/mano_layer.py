@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from .mano_extras import SphereVariants
 
 # joint re-orderings from MANO to each dataset's skeleton (same tables as the reference, :36-81)
 MANO2HANDS = [0, 13, 1, 4, 10, 7, 14, 15, 20, 2, 3, 16, 5, 6, 17, 11, 12, 19, 8, 9, 18]
@@ -167,7 +168,7 @@ class _CollFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # MANO layer
 # ------------------------------------------------------------------------------------------------
-class MANO_SMPL(nn.Module):
+class MANO_SMPL(SphereVariants, nn.Module):
     """B200-native replacement of the reference ``MANO_SMPL`` (mano_layer.py:82-770)."""
 
     def __init__(self, mano_pkl_path, dataset, scale=1000):
@@ -702,14 +703,92 @@ class Render(nn.Module):
         return torch.stack((u, v, joint_xyz[:, :, 2]), dim=-1)
 
     def mask_img(self, img, img_joint, mask_offset, mask_para, min_mask_num=3, max_mask_num=10):
-        """Random spherical occluders around a few joints (non-differentiable augmentation, :1326-1340)."""
+        """Random spherical occluders around a few joints (non-differentiable augmentation, :1326-1340).
+        The random numbers are drawn with the reference's own calls in its order (numpy choice twice, torch.rand
+        on the CPU twice), so equal seeds give equal occluders; the masking itself is one kernel (dsf_mask_img)
+        instead of a (B, mask_num, R*R) distance tensor."""
         device = img.device
         b, j, _ = img_joint.size()
         mask_num = int(np.random.choice(np.arange(min_mask_num, max_mask_num), 1, replace=False)[0])
         joint_id = np.random.choice(np.arange(0, j), mask_num, replace=False)
         centre = img_joint[:, joint_id, :] + ((torch.rand(b, mask_num, 3) - 0.5) * mask_offset * 2).to(device)
         radius = torch.rand([b, mask_num]).to(device) * mask_para
-        pts = torch.cat((self.xy_mesh.view(1, -1, 2).repeat(b, 1, 1), img.view(b, -1, 1)), dim=-1)
-        dis = torch.sqrt(((pts.view(b, 1, -1, 3) - centre.view(b, mask_num, 1, 3)) ** 2).sum(-1))
-        keep = ~(dis < radius.view(b, mask_num, 1)).any(1)
-        return torch.where(keep.view(b, 1, img.size(-2), img.size(-1)), img, torch.ones_like(img))
+        return self.mask_spheres(img, centre, radius)
+
+    def mask_spheres(self, img, centres, radii):
+        """The deterministic part of mask_img: pixels inside any sphere (centres (B,n,3), radii (B,n)) -> 1.0."""
+        img_c = L.f32c(img.detach())
+        R = img_c.shape[-1]
+        if img_c.shape[-2] != R:
+            raise ValueError("square images only")
+        B = img_c.numel() // (R * R)
+        centres, radii = L.f32c(centres.detach()), L.f32c(radii.detach())
+        out = torch.empty_like(img_c)
+        L.check(L.lib().dsf_mask_img(B, R, img_c.data_ptr(), int(radii.shape[1]), centres.data_ptr(), radii.data_ptr(),
+                                     out.data_ptr(), L.stream_ptr()))
+        return out
+
+    def synth2real(self, noraml_img, noise=0.1, noise_patch=2, sigma=1.7, bk_value=0.95):
+        """:1222-1231 - patch-wise white noise on the foreground, then a 5x5 Gaussian on the reflect-padded image
+        (one kernel, dsf_synth2real).  The reference reads ``self.smoothing``, which it never assigns; the
+        filter is its own ``GaussianSmoothing(5)`` (:808-868), the only reading under which the 2-pixel padding
+        gives back an image of the same size.  The noise is drawn like the reference does (torch.randn on the
+        CPU), so equal seeds give equal images."""
+        B, C_, H, W = noraml_img.size()
+        if C_ != 1 or H != W:
+            raise ValueError("expected (B,1,R,R)")
+        img_c = L.f32c(noraml_img.detach())
+        nz = L.f32c(noise * torch.randn((B, C_, H // noise_patch, W // noise_patch)))
+        out = torch.empty_like(img_c)
+        L.check(L.lib().dsf_synth2real(B, H, img_c.data_ptr(), nz.data_ptr(), int(noise_patch), float(bk_value),
+                                       float(sigma), out.data_ptr(), L.stream_ptr()))
+        return out
+
+    # -- resampling helpers of the reference's own pixel chain (:1233-1287); Render itself never materialises
+    #    the 640^2 raster, these exist for callers that hold full-size images -------------------------
+    def resize(self, img):
+        """:1233-1242 - nearest resample of (B,C,S,S) to the sensor size (H,W)."""
+        import torch.nn.functional as F
+        b = img.size(0)
+        theta = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]], device=img.device).unsqueeze(0).repeat(b, 1, 1)
+        grid = F.affine_grid(theta, [b, 1, int(self.img_size[1]), int(self.img_size[0])], align_corners=False)
+        return F.grid_sample(img, grid, mode="nearest", align_corners=False)
+
+    def affine_grid(self, img, M):
+        """:1244-1255 - sampling grid of the crop: crop pixel (cx, cy) reads sensor position M^-1 (cx, cy, 1)."""
+        b, _, h_ori, w_ori = img.size()
+        R = self.crop_size[0]
+        ii = torch.arange(R, device=img.device, dtype=torch.float32)
+        yy, xx = torch.meshgrid(ii, ii, indexing="ij")
+        mesh = torch.stack((xx, yy, torch.ones_like(xx)), -1).reshape(1, -1, 3, 1)
+        pts = torch.matmul(torch.inverse(M).view(b, 1, 3, 3), mesh).squeeze(-1)[:, :, 0:2]
+        scale = torch.tensor([w_ori, h_ori], device=img.device, dtype=torch.float32).view(1, 1, 2)
+        return (pts / scale * 2 - 1).view(b, R, R, 2)
+
+    def warpPerspective(self, img, M):
+        """:1257-1260 - nearest crop of a sensor-size image through M."""
+        import torch.nn.functional as F
+        return F.grid_sample(img, self.affine_grid(img, M), mode="nearest", align_corners=False)
+
+    def ResizeRenderImg(self, img):
+        """:1262-1273 - RoIAlign (sampling_ratio 1, one bilinear sample per output pixel) of the square raster to
+        the sensor size: output pixel (r, c) samples ((c + .5) S / W - .5, (r + .5) S / H - .5)."""
+        import torch.nn.functional as F
+        b = img.size(0)
+        S = float(max(self.img_size))
+        W, H = int(self.img_size[0]), int(self.img_size[1])
+        xs = (torch.arange(W, device=img.device, dtype=torch.float32) + 0.5) * (S / W) - 0.5
+        ys = (torch.arange(H, device=img.device, dtype=torch.float32) + 0.5) * (S / H) - 0.5
+        gx = (xs + 0.5) / img.size(-1) * 2 - 1
+        gy = (ys + 0.5) / img.size(-2) * 2 - 1
+        grid = torch.stack((gx.view(1, W).expand(H, W), gy.view(H, 1).expand(H, W)), -1).unsqueeze(0).repeat(b, 1, 1, 1)
+        return F.grid_sample(img, grid, mode="bilinear", padding_mode="border", align_corners=False)
+
+    def massCenter(self, img):
+        """:1275-1287 - (u, v, depth) centroid of the positive pixels of (B,1,H,W)."""
+        b, _, h, w = img.size()
+        yv, xv = torch.meshgrid(torch.arange(h, device=img.device, dtype=torch.float32),
+                                torch.arange(w, device=img.device, dtype=torch.float32), indexing="ij")
+        fg = img.gt(0).float()
+        pts = torch.cat((xv.expand(b, 1, h, w), yv.expand(b, 1, h, w), img), dim=1) * fg
+        return pts.mean(-1).mean(-1) / fg.mean(-1).mean(-1)

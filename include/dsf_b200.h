@@ -348,6 +348,33 @@ int dsf_rotate_points_backward(int batch, int n, const float* pts, const float* 
                                const float* g_out, float* g_pts, float* g_R, float* g_center,
                                dsfStream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * "next" row f4 - the synthetic-data generator extras of Render.forward / M_render and the chamfer loss.
+ *
+ * dsf_mask_img replaces Render.mask_img (render_model/mano_layer.py:1326-1340): pixel (row, col) of the (B,R,R)
+ * normalised crop, seen as the point (2 (col + .5) / R - 1, 2 (row + .5) / R - 1, depth), becomes background 1.0
+ * when it lies strictly inside one of the hand's n_mask <= 32 spheres (centres (B,n_mask,3), radii (B,n_mask));
+ * the random choice of joints / offsets / radii stays with the host wrapper, which draws them with the
+ * reference's own generator calls.  out may alias img.
+ *
+ * dsf_synth2real replaces Render.synth2real (:1222-1231): img + upsample_nearest(noise (B,R/patch,R/patch)) on
+ * the foreground (img < bk_value), then - sigma != 0 - reflect padding by 2 and the normalised 5x5 Gaussian of
+ * GaussianSmoothing (:808-868) in one pass.  noise may be NULL.  out must not alias img.
+ *
+ * dsf_chamfer_forward / _backward: nearest neighbour (squared distance, index; lowest index on ties) of every
+ * point of x (B,P1,3) in y (B,P2,3) and vice versa - the K = 1 knn_points core of pytorch3d's chamfer_distance as
+ * surface_loss.forward uses it (render_model/render_loss.py:44-52); backward takes d loss / d dist_x, d dist_y and
+ * writes d loss / d x, d y (overwritten). */
+int dsf_mask_img(int batch, int R, const float* img, int n_mask, const float* centres, const float* radii,
+                 float* out, dsfStream_t stream);
+int dsf_synth2real(int batch, int R, const float* img, const float* noise, int patch, float bk_value,
+                   float sigma, float* out, dsfStream_t stream);
+int dsf_chamfer_forward(int batch, int P1, int P2, const float* x, const float* y, float* dist_x, int* idx_x,
+                        float* dist_y, int* idx_y, dsfStream_t stream);
+int dsf_chamfer_backward(int batch, int P1, int P2, const float* x, const float* y, const int* idx_x,
+                         const int* idx_y, const float* g_dist_x, const float* g_dist_y, float* g_x, float* g_y,
+                         dsfStream_t stream);
+
 /* number of kernel launches the last call on this thread enqueued (bench.py's gpu_launches) */
 int dsf_last_launch_count(void);
 
