@@ -508,11 +508,45 @@ def run_ours(args):
         for fn in (icp, coll):
             fn()
         t_icp, t_coll = time_region(icp, 5), time_region(coll, 20)
-        pairs = b4 * P * layer.faces_int.shape[0]
-        other["C4_icp_batch1024"] = {"hands": b4, "points": P, "faces": int(layer.faces_int.shape[0]),
-                                     "ms_fwd_bwd": t_icp, "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
-                                     "note": "ICPLoss fwd+bwd; exhaustive scan with a per-face bounding-sphere cull over spatially ordered points (rate counts all point-face pairs); FP32 compute bound, bytes negligible"}
-        other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3)}
+
+        def icp_fwd():
+            _PointFaceDistance.apply(pcl, v4.detach(), layer.faces_int)
+
+        icp_fwd()
+        t_icp_fwd = time_region(icp_fwd, 5)
+        # FP32 roofline of the point-face scan (compute bound, bytes negligible): work counters of
+        # the same launch, flops per pair as documented at dsf_point_face_stats
+        from dsf_b200 import _lib as _L
+        nF = int(layer.faces_int.shape[0])
+        st3 = torch.zeros(3, dtype=torch.int64, device=dev)
+        dd = torch.empty(b4, P, device=dev)
+        ii = torch.empty(b4, P, dtype=torch.int32, device=dev)
+        oo = torch.empty(b4, P, dtype=torch.int32, device=dev)
+        vv = v4.detach().contiguous()
+        _L.check(_L.lib().dsf_point_face_stats(b4, P, vv.shape[1], nF, pcl.data_ptr(), vv.data_ptr(),
+                                               layer.faces_int.data_ptr(), dd.data_ptr(), ii.data_ptr(), oo.data_ptr(),
+                                               st3.data_ptr(), _L.stream_ptr()))
+        n_cull, n_in, n_edge = (int(x) for x in st3.tolist())
+        pairs = b4 * P * nF
+        flops = 15 * n_cull + 47 * n_in + 143 * n_edge
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        other["C4_icp_batch1024"] = {
+            "hands": b4, "points": P, "faces": nF, "ms_fwd_bwd": t_icp, "ms_fwd": t_icp_fwd,
+            "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
+            "pairs": {"all": pairs, "sphere_culled": n_cull, "evaluated_interior": n_in, "evaluated_edge": n_edge,
+                      "evaluated_frac": (n_in + n_edge) / pairs},
+            "roofline": {"bound": "fp32", "kernel": "point_face_fwd_kernel", "achieved": flops / (t_icp_fwd * 1e-3) / 1e12,
+                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / (t_icp_fwd * 1e-3) / 1e12 / fp32_peak,
+                         "flops_per_launch": flops,
+                         "flops_per_pair": {"sphere_test": 15, "interior": 47, "edge": 143},
+                         "peak_source": "148 SMs x 128 FP32 lanes x 2 (FMA) x 1.965 GHz; ms_fwd includes the point "
+                                        "sort launch (< 3 % of it)",
+                         "brute_force_equivalent": pairs * 143 / (t_icp_fwd * 1e-3) / 1e12},
+            "note": "ICPLoss fwd+bwd; exhaustive scan with a per-face bounding-sphere cull over spatially ordered points; "
+                    "FP32 compute bound, bytes negligible"}
+        other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3),
+                                      "note": "latency bound: one warp per hand, 9.6 KB in per hand = %.0f GB/s"
+                                              % (b4 * 9600 / (t_coll * 1e-3) / 1e9)}
         # the reference's own call sequence through the drop-in classes: Render.render -> m2d loss -> backward
         # (one autograd node + the loss op), literal 640^2 -> 480x640 -> 128^2 pixel chain, batch 128 (configs[1])
         from dsf_b200.mano_layer import Render as _Render

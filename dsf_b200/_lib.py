@@ -68,6 +68,7 @@ SIGNATURES = {
     "dsf_depth_loss": (_I, [_I, _I, _I, _VP, _VP, _F, _F, _VP, _VP, _VP, _VP]),
     "dsf_coll_forward_backward": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_point_face_forward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dsf_point_face_stats": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_point_face_backward": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_sphere_set": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_seg_pcl": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP]),

@@ -187,10 +187,14 @@ point_sort_kernel(int P, const float* __restrict__ points, int* __restrict__ ord
     for (int i = tid; i < P; i += PS_THREADS) order[(size_t)b * P + atomicAdd(&s_hist[cell(i)], 1)] = i;
 }
 
+// STATS: the same scan, additionally counting per category how many (point, face) pairs were only sphere-tested,
+// evaluated on the interior branch, and evaluated on the edge branch (bench.py's FP32 roofline of config C4)
+template <bool STATS>
 __global__ void __launch_bounds__(PF_THREADS)
 point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, const float* __restrict__ verts,
                       const int* __restrict__ faces, const int* __restrict__ order, float* __restrict__ dists,
-                      int* __restrict__ idxs) {
+                      int* __restrict__ idxs, unsigned long long* __restrict__ stats) {
+    unsigned int n_cull = 0, n_in = 0, n_edge = 0;
     __shared__ __align__(16) float s_rec[PF_CHUNK * PF_REC];
     const int b = blockIdx.y;
     const int slot = blockIdx.x * PF_THREADS + threadIdx.x;
@@ -216,7 +220,7 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
             // (and, with the strict < below, the arg-min) is the brute-force one.
             const V3 ac = a - v3(q5.x, q5.y, q5.z);
             const float reach = sb + q5.w;
-            if (dot(ac, ac) > reach * reach * 1.0002f + 1e-30f) continue;
+            if (dot(ac, ac) > reach * reach * 1.0002f + 1e-30f) { if (STATS && live) ++n_cull; continue; }
             const float4 q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
             const V3 e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
             const V3 nh = v3(q2.y, q2.z, q2.w);
@@ -229,7 +233,9 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
             float d;
             if (q4.w != 0.f && w0 >= 0.f && w0 <= 1.f && w1 >= 0.f && w1 <= 1.f && w2 >= 0.f && w2 <= 1.f) {
                 d = t * t;
+                if (STATS && live) ++n_in;
             } else {
+                if (STATS && live) ++n_edge;
                 const float e01 = seg_d2(a, e1, q4.x);
                 const float e02 = seg_d2(a, e2, q4.y);
                 const float e12 = seg_d2(a - e1, e2 - e1, q4.z);
@@ -241,6 +247,15 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
     if (live) {
         dists[(size_t)b * P + pi] = best;
         idxs[(size_t)b * P + pi] = bi;
+    }
+    if (STATS) {
+        unsigned int c[3] = {n_cull, n_in, n_edge};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+            if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(stats + k, (unsigned long long)c[k]);
+        }
     }
 }
 
@@ -328,8 +343,30 @@ extern "C" int dsf_point_face_forward(int batch, int P, int V, int F, const floa
         DSF_CHECK_LAUNCH();
     }
     dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
-    point_face_fwd_kernel<<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws, dists,
-                                                                       idxs);
+    point_face_fwd_kernel<false><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
+                                                                              dists, idxs, nullptr);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// Work counters of the forward scan for the same inputs: stats[0] = pairs rejected by the bounding-sphere test,
+// [1] = pairs evaluated on the interior branch, [2] = on the edge branch (device, 3 x uint64, overwritten).
+// Per pair the scan spends 15 flops on the sphere test, 32 more for the plane projection + barycentrics of an
+// interior hit, 96 more when the three edge distances are needed (multiply, add and compare each count one).
+extern "C" int dsf_point_face_stats(int batch, int P, int V, int F, const float* points, const float* verts,
+                                    const int* faces, float* dists, int* idxs, int* order_ws,
+                                    unsigned long long* stats, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(points && verts && faces && dists && idxs && stats, "null argument");
+    DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0 && F > 0, "sizes");
+    DSF_CHECK_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream));
+    if (order_ws) {
+        point_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(P, points, order_ws);
+        DSF_CHECK_LAUNCH();
+    }
+    dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
+    point_face_fwd_kernel<true><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
+                                                                             dists, idxs, stats);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

@@ -192,6 +192,12 @@ int dsf_coll_forward_backward(const DsfMano* h, int batch, const float* joints, 
  * culls whole warps; results are identical either way (the brute-force minimum and arg-min). */
 int dsf_point_face_forward(int batch, int P, int V, int F, const float* points, const float* verts,
                            const int* faces, float* dists, int* idxs, int* order_ws, dsfStream_t stream);
+/* dsf_point_face_forward plus work counters for the FP32 roofline of this (compute-bound) row: stats (device,
+ * 3 x uint64, overwritten) = pairs rejected by the bounding-sphere test | evaluated, interior branch | evaluated,
+ * edge branch. */
+int dsf_point_face_stats(int batch, int P, int V, int F, const float* points, const float* verts,
+                         const int* faces, float* dists, int* idxs, int* order_ws, unsigned long long* stats,
+                         dsfStream_t stream);
 int dsf_point_face_backward(int batch, int P, int V, int F, const float* points, const float* verts,
                             const int* faces, const int* idxs, const float* g_dists,
                             float* g_points, float* g_verts, dsfStream_t stream);

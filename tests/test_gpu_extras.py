@@ -121,7 +121,12 @@ def test_resampling_helpers_match_reference_golden(rnd, ex, crop_in):
     sensor = rnd.resize(idx_img)
     assert sensor.shape == (2, 1, 480, 640)
     got, ref = sensor[:, :, ::7, ::5].cpu().numpy(), ex["resize_sub"]
-    assert (got != ref).mean() < 0.02            # .5 rounding rows of the 640 -> 480 nearest resize (tie class T3)
+    # sensor row r reads raster row (2 r + 1) * 2 / 3 - 1 / 2: an exact .5 for r = 1 (mod 3), which grid_sample
+    # rounds by float noise (tie class T3; CPU and GPU builds of torch disagree there) - every other row is exact
+    rows = np.arange(0, 480, 7)
+    clean = rows % 3 != 1
+    assert np.array_equal(got[:, :, clean], ref[:, :, clean])
+    assert (got != ref).mean() < 0.34
     M = torch.tensor(ex["helpers_M"]).cuda()
     np.testing.assert_allclose(rnd.affine_grid(sensor, M)[:, ::9, ::9].cpu().numpy(), ex["affine_grid_sub"], atol=2e-5)
     ref_sensor = sensor.clone()
