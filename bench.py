@@ -528,7 +528,7 @@ def run_ours(args):
                                                st3.data_ptr(), _L.stream_ptr()))
         n_cull, n_in, n_edge = (int(x) for x in st3.tolist())
         pairs = b4 * P * nF
-        flops = 15 * n_cull + 47 * n_in + 143 * n_edge
+        flops = 16 * n_cull + 56 * n_in + 120 * n_edge
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         other["C4_icp_batch1024"] = {
             "hands": b4, "points": P, "faces": nF, "ms_fwd_bwd": t_icp, "ms_fwd": t_icp_fwd,
@@ -538,10 +538,10 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "kernel": "point_face_fwd_kernel", "achieved": flops / (t_icp_fwd * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / (t_icp_fwd * 1e-3) / 1e12 / fp32_peak,
                          "flops_per_launch": flops,
-                         "flops_per_pair": {"sphere_test": 15, "interior": 47, "edge": 143},
+                         "flops_per_pair": {"sphere_test": 16, "interior": 56, "edge": 120},
                          "peak_source": "148 SMs x 128 FP32 lanes x 2 (FMA) x 1.965 GHz; ms_fwd includes the point "
                                         "sort launch (< 3 % of it)",
-                         "brute_force_equivalent": pairs * 143 / (t_icp_fwd * 1e-3) / 1e12},
+                         "brute_force_equivalent": pairs * 120 / (t_icp_fwd * 1e-3) / 1e12},
             "note": "ICPLoss fwd+bwd; exhaustive scan with a per-face bounding-sphere cull over spatially ordered points; "
                     "FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3),

@@ -351,8 +351,9 @@ extern "C" int dsf_point_face_forward(int batch, int P, int V, int F, const floa
 
 // Work counters of the forward scan for the same inputs: stats[0] = pairs rejected by the bounding-sphere test,
 // [1] = pairs evaluated on the interior branch, [2] = on the edge branch (device, 3 x uint64, overwritten).
-// Per pair the scan spends 15 flops on the sphere test, 32 more for the plane projection + barycentrics of an
-// interior hit, 96 more when the three edge distances are needed (multiply, add and compare each count one).
+// Per pair the scan spends 16 flops on the sphere test (p - v0, offset to the sphere centre, squared norm, reach),
+// 40 more for the plane projection + barycentrics + range checks of an interior hit (56), and 64 more when the
+// three clamped edge distances are needed instead of t^2 (120); multiply, add and compare each count one.
 extern "C" int dsf_point_face_stats(int batch, int P, int V, int F, const float* points, const float* verts,
                                     const int* faces, float* dists, int* idxs, int* order_ws,
                                     unsigned long long* stats, dsfStream_t stream) {
