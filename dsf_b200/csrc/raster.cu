@@ -84,12 +84,15 @@ __global__ void view_setup_kernel(int mode, int B, const float* __restrict__ cen
         vw[5] = zh;
         vw[6] = __fdiv_rn(__fsub_rn(__fadd_rn(cz, zh), cz), zh);   // background after normalize_img
         vw[15] = 0.f;
-        vw[16] = (float)(mode == 0 ? R : (W > H ? W : H));   // side of the raster the samples index into
+        vw[16] = (float)(mode != 1 ? R : (W > H ? W : H));   // side of the raster the samples index into
         vw[17] = 0.f; vw[18] = 0.f; vw[19] = 0.f;
-        if (mode == 0) {
+        if (mode != 1) {
             float half = (float)R * 0.5f;
             float fxc = __fmul_rn(sM[0], fx), fyc = __fmul_rn(sM[2], fy);
             float pxc = __fadd_rn(__fmul_rn(sM[0], px), sM[1]), pyc = __fadd_rn(__fmul_rn(sM[2], py), sM[3]);
+            // mode 2: sample i sits at crop coordinate i (the convention of M, JointTrans and the literal chain,
+            // whose crop index c reads sensor coordinate (c - t) / s) instead of the pixel centre i + 1/2
+            if (mode == 2) { pxc = __fadd_rn(pxc, 0.5f); pyc = __fadd_rn(pyc, 0.5f); }
             vw[0] = __fdiv_rn(fxc, half);
             vw[1] = __fdiv_rn(fyc, half);
             vw[2] = -__fdiv_rn(__fsub_rn(pxc, half), half);
@@ -110,7 +113,7 @@ __global__ void view_setup_kernel(int mode, int B, const float* __restrict__ cen
         s_lo[0] = s_lo[1] = R; s_hi[0] = s_hi[1] = -1;
     }
     __syncthreads();
-    if (mode == 0) {
+    if (mode != 1) {
         for (int i = threadIdx.x; i < R; i += blockDim.x) {
             float v = pix_to_ndc(i, R);
             xs[(size_t)b * R + i] = v;
@@ -150,7 +153,7 @@ extern "C" int dsf_view_setup(int mode, int batch, const float* center3d, const 
                               const float* intr4, int W, int H, int R, const float* M_in, float* view,
                               float* xs, float* ys, float* M_out, dsfStream_t stream) {
     dsf_reset_launch_count();
-    DSF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (direct) or 1 (literal)");
+    DSF_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (direct), 1 (literal) or 2 (direct, index-aligned)");
     DSF_REQUIRE(batch > 0 && center3d && cube && intr4 && view && xs && ys, "null argument");
     DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
     DSF_REQUIRE(W > 0 && H > 0, "sensor size");

@@ -12,6 +12,12 @@ import torch
 from . import _lib as L
 
 
+# sampling modes of dsf_view_setup: "direct" = R x R raster sampled at crop pixel centres (benchmark configs),
+# "literal" = the reference's 640^2 -> resize -> crop chain, "direct_aligned" = direct raster whose sample i sits at
+# crop coordinate i, i.e. registered with M / JointTrans / loader-cropped depth (no half-pixel offset)
+_MODES = {"direct": 0, "literal": 1, "direct_aligned": 2}
+
+
 class FitStep:
     """One fitting step over a resident batch.
 
@@ -26,7 +32,7 @@ class FitStep:
                  perspective_correct=False, keep_pix_to_face=True):
         self.lib = L.lib()
         self.flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
-        if mode != "direct":
+        if mode == "literal":
             # literal 640-pixel raster: float32 sample coordinates are not exactly 1 - (2 q + 1) / S there, keep
             # the per-pixel backward kernel (see DSF_RASTER_SEPARATE_BACKWARD)
             self.flags |= L.RASTER_SEPARATE_BACKWARD
@@ -34,7 +40,7 @@ class FitStep:
             raise ValueError("only the direct-mode, non-perspective-correct step can drop the pix_to_face plane")
         self.layer = mano_layer
         self.B, self.R = int(batch), int(crop)
-        self.mode = 0 if mode == "direct" else 1
+        self.mode = _MODES[mode]
         self.loss_weight = float(loss_weight)
         self.dev = device or mano_layer.v_template.device
         self.W, self.H = int(image_size[0]), int(image_size[1])
@@ -184,13 +190,13 @@ class MultiViewFitStep:
                  perspective_correct=False, keep_pix_to_face=True):
         self.lib = L.lib()
         self.flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
-        if mode != "direct":
+        if mode == "literal":
             self.flags |= L.RASTER_SEPARATE_BACKWARD
         if self.flags and not keep_pix_to_face:
             raise ValueError("only the direct-mode, non-perspective-correct step can drop the pix_to_face plane")
         self.layer = mano_layer
         self.B, self.V, self.R = int(batch), int(views), int(crop)
-        self.mode = 0 if mode == "direct" else 1
+        self.mode = _MODES[mode]
         self.loss_weight = float(loss_weight)
         self.dev = device or mano_layer.v_template.device
         self.W, self.H = int(image_size[0]), int(image_size[1])

@@ -110,7 +110,11 @@ int dsf_mano_backward(const DsfMano* h, int batch, const DsfManoParams* p, float
  * R0/R3  per-hand camera + crop set-up - replaces Render.points3DToImg / comToBounds /
  * Offset2Trans / resize / affine_grid (mano_layer.py:1318-1324, :1133-1169, :1233-1260) and
  * the pytorch3d PerspectiveCameras / RasterizationSettings built at :939-952.
- * mode 0 "direct": R x R raster with crop-space intrinsics, samples at crop pixel centres.
+ * mode 0 "direct": R x R raster with crop-space intrinsics, samples at crop pixel centres (i + 1/2; what a
+ *         pytorch3d MeshRasterizer of image_size R with those intrinsics does - BASELINE's benchmark configs).
+ * mode 2 "direct, index-aligned": the same raster with the principal point moved by half a crop pixel, so that
+ *         sample i sits at crop coordinate i - the convention of M, JointTrans and of the literal chain, whose
+ *         crop index c reads sensor coordinate (c - t) / s.  Use it to fit crops the data loader cut with M.
  * mode 1 "literal": the S x S raster -> (H,W) resize -> crop chain, evaluated only at the
  *         raster pixel each crop pixel reads (S = max(W,H)); M_in (B,3,3) optional (M_render /
  *         getDepth pass their own, must be axis-aligned), else recomputed like render() does.

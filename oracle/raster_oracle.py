@@ -68,10 +68,12 @@ def make_view(mode, center3d, cube, intr, W, H, crop, S=None):
     view[:, 4] = zc
     view[:, 5] = zh
     view[:, 6] = ((zc + zh) - zc) / zh            # what normalize_img (:1289-1299) gives background
-    if mode == "direct":
+    if mode in ("direct", "direct_aligned"):
         s = M[:, 0, 0]
         fxc, fyc = s * fx, s * fy
         pxc, pyc = s * px + M[:, 0, 2], s * py + M[:, 1, 2]
+        if mode == "direct_aligned":        # sample i at crop coordinate i (M's convention), not i + 1/2
+            pxc, pyc = pxc + 0.5, pyc + 0.5
         half = crop / 2.
         view[:, 0] = fxc / half
         view[:, 1] = fyc / half
