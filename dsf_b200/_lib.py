@@ -91,6 +91,8 @@ SIGNATURES = {
     "dsf_crop_hand": (_I, [_I, _I, _VP, _VP, _I, _VP, _VP, _VP, c_float_p, _F, _F, _F, _VP, _VP, _VP]),
     "dsf_img2pcl": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, c_float_p, _F, _F, _I, C.c_ulonglong, _VP, _VP, _VP]),
     "dsf_target_from_u16": (_I, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP]),
+    "dsf_target_from_u16_rows": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
+    "dsf_pack_u16_rows": (_L, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _L]),
     "dsf_intersect_workspace_bytes": (C.c_long, [_I, _I, _I, _I]),
     "dsf_intersect_vox": (_I, [_I, _I, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dsf_rotate_points": (_I, [_I, _I, _VP, _VP, _VP, _VP, _VP]),

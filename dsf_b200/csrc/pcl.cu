@@ -372,3 +372,101 @@ extern "C" int dsf_target_from_u16(int batch, int R, const unsigned short* depth
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Row-run transport of the sensor crop ("data formats either side of the path"): ~80 % of a hand crop is
+// background, so the loader can ship, per row, only the span between the first and the last pixel that is not
+// background (depth 0 / invalid marker / at or beyond the far plane of the cube): rows (B,R,2) uint16 =
+// (first column, length), hand_offset (B+1) uint32 = start of each hand's pixels in the packed uint16 payload.
+// The kernel rebuilds the normalised fp32 target, bit-identical to dsf_target_from_u16 on the unpacked crop:
+// inside a span the same target_norm, outside it the background value target_norm gives depth 0.
+// One CTA per hand: warp-scan of the row lengths, then each warp writes whole rows (coalesced).
+// ------------------------------------------------------------------------------------------------
+#define RR_THREADS 256
+#define RR_MAXR 512
+
+__global__ void __launch_bounds__(RR_THREADS)
+target_from_u16_rows_kernel(int R, const unsigned short* __restrict__ rows, const unsigned int* __restrict__ hand_offset,
+                            const unsigned short* __restrict__ payload, const float* __restrict__ center,
+                            const float* __restrict__ cube, unsigned invalid, float* __restrict__ out) {
+    __shared__ unsigned int s_off[RR_MAXR + 1];
+    __shared__ unsigned int s_warp[RR_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned short* rt = rows + (size_t)b * R * 2;
+    // exclusive scan of the row lengths (R <= 512: two rows per thread)
+    const int r0 = 2 * tid, r1 = 2 * tid + 1;
+    const unsigned int l0 = r0 < R ? rt[2 * r0 + 1] : 0u, l1 = r1 < R ? rt[2 * r1 + 1] : 0u;
+    unsigned int incl = l0 + l1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int base = hand_offset[b];
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    const unsigned int ex = base + incl - (l0 + l1);
+    if (r0 < R) s_off[r0] = ex;
+    if (r1 < R) s_off[r1] = ex + l0;
+    __syncthreads();
+    const float cz = center[3 * b + 2], hz = __fdiv_rn(cube[3 * b + 2], 2.f);
+    const float far_ = __fadd_rn(cz, hz), near_ = __fsub_rn(cz, hz);
+    const float bg = target_norm(0u, invalid, cz, hz, far_, near_);
+    float* o = out + (size_t)b * R * R;
+    for (int r = warp; r < R; r += RR_THREADS / 32) {
+        const int c0 = rt[2 * r], n = rt[2 * r + 1];
+        const unsigned short* src = payload + s_off[r];
+        for (int c = lane; c < R; c += 32) {
+            const int k = c - c0;
+            o[(size_t)r * R + c] = (k >= 0 && k < n) ? target_norm(src[k], invalid, cz, hz, far_, near_) : bg;
+        }
+    }
+}
+
+extern "C" int dsf_target_from_u16_rows(int batch, int R, const unsigned short* rows, const unsigned int* hand_offset,
+                                        const unsigned short* payload, const float* center3d, const float* cube,
+                                        int invalid_value, float* target, dsfStream_t stream) {
+    dsf_reset_launch_count();
+    DSF_REQUIRE(batch > 0 && R >= 2 && R <= RR_MAXR && rows && hand_offset && payload && center3d && cube && target,
+                "null / empty argument (R <= 512)");
+    DSF_REQUIRE(invalid_value >= 0 && invalid_value <= 65535, "invalid_value must fit uint16 (0 = none)");
+    target_from_u16_rows_kernel<<<batch, RR_THREADS, 0, (cudaStream_t)stream>>>(
+        R, rows, hand_offset, payload, center3d, cube, (unsigned)invalid_value, target);
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
+}
+
+// The loader's side of that format (host code, no device involved): pack (B,R,R) uint16 millimetre crops.
+// rows (B,R,2), hand_offset (B+1), payload (capacity payload_cap pixels).  Returns the number of payload pixels,
+// or -1 when the capacity is too small.  A pixel is background when it is 0, the invalid marker, or at / beyond the
+// far plane center_z + cube_z / 2 evaluated in float32 exactly like the kernel does.
+extern "C" long dsf_pack_u16_rows(int batch, int R, const unsigned short* depth_mm, const float* center3d,
+                                  const float* cube, int invalid_value, unsigned short* rows,
+                                  unsigned int* hand_offset, unsigned short* payload, long payload_cap) {
+    if (batch <= 0 || R < 2 || R > RR_MAXR || !depth_mm || !center3d || !cube || !rows || !hand_offset || !payload)
+        return -1;
+    long n = 0;
+    for (int b = 0; b < batch; ++b) {
+        hand_offset[b] = (unsigned int)n;
+        const volatile float hz = cube[3 * b + 2] / 2.f;            // float32 steps, as in target_norm
+        const volatile float far_ = center3d[3 * b + 2] + hz;
+        for (int r = 0; r < R; ++r) {
+            const unsigned short* row = depth_mm + ((size_t)b * R + r) * R;
+            int first = R, last = -1;
+            for (int c = 0; c < R; ++c) {
+                const unsigned u = row[c];
+                const bool bgp = u == 0u || (invalid_value && u == (unsigned)invalid_value) || (float)u >= far_;
+                if (!bgp) { if (first == R) first = c; last = c; }
+            }
+            const int len = last >= first ? last - first + 1 : 0;
+            rows[((size_t)b * R + r) * 2] = (unsigned short)(len ? first : 0);
+            rows[((size_t)b * R + r) * 2 + 1] = (unsigned short)len;
+            if (n + len > payload_cap) return -1;
+            for (int c = 0; c < len; ++c) payload[n + c] = row[first + c];
+            n += len;
+        }
+    }
+    hand_offset[batch] = (unsigned int)n;
+    return n;
+}

@@ -52,6 +52,7 @@ class FitStep:
         self.cube = f(B, 3)
         self.target = f(B, R, R)
         self.target_u16 = None            # allocated on first use (set_inputs with a uint16 target)
+        self._row_bufs = None             # ... with a row-run packed target
         self.view = f(B, L.VIEW_STRIDE)
         self.xs = f(B, R)
         self.ys = f(B, R)
@@ -94,7 +95,16 @@ class FitStep:
         self.cube.copy_(cube, non_blocking=True)
         self._view_setup()                       # view records / sample grids follow (center3d, cube)
         if target is not None:
-            if target.dtype == torch.uint16:
+            from .pcl import RowRunTarget, target_from_u16_rows
+            if isinstance(target, RowRunTarget):
+                # row-run packed sensor crop: only the non-background span of every row travels over PCIe
+                if self._row_bufs is None:
+                    dev = self.target.device
+                    self._row_bufs = (torch.empty(self.B, self.R, 2, dtype=torch.uint16, device=dev),
+                                      torch.empty(self.B + 1, dtype=torch.int32, device=dev),
+                                      torch.empty(self.B * self.R * self.R, dtype=torch.uint16, device=dev))
+                target_from_u16_rows(target, self.center3d, self.cube, 0, out=self.target, buffers=self._row_bufs)
+            elif target.dtype == torch.uint16:
                 # sensor format: uint16 millimetres travel over PCIe (half the bytes), normalised here
                 if self.target_u16 is None:
                     self.target_u16 = torch.empty(self.B, self.R, self.R, dtype=torch.uint16, device=self.target.device)

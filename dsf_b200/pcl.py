@@ -74,3 +74,70 @@ def target_from_u16(depth_mm, center, cube, invalid_value=0, out=None):
     L.check(lib.dsf_target_from_u16(B, R, depth_mm.data_ptr(), center.data_ptr(), cube.data_ptr(),
                                     int(invalid_value), out.data_ptr(), L.stream_ptr()))
     return out
+
+
+class RowRunTarget:
+    """Host-side row-run packing of sensor crops (the loader's output format for dsf_target_from_u16_rows): per row
+    only the span from the first to the last non-background pixel.  rows (B,R,2) uint16 = (first column, length),
+    hand_offset (B+1) int32 (pixels), payload (n,) uint16 - pinned CPU tensors unless ``pin=False``."""
+
+    def __init__(self, rows, hand_offset, payload, R):
+        self.rows, self.hand_offset, self.payload, self.R = rows, hand_offset, payload, int(R)
+
+    @property
+    def batch(self):
+        return self.rows.shape[0]
+
+    @property
+    def nbytes(self):
+        return self.rows.numel() * 2 + self.hand_offset.numel() * 4 + self.payload.numel() * 2
+
+
+def pack_target_rows(depth_mm, center, cube, invalid_value=0, pin=True):
+    """(B,R,R) uint16 millimetre crops (CPU tensor or ndarray) -> RowRunTarget.  Runs the library's host packer
+    (dsf_pack_u16_rows; no device involved): this is work for the data loader, once per sample."""
+    import numpy as np
+
+    lib = L.load_library()
+    d = depth_mm.cpu().numpy() if isinstance(depth_mm, torch.Tensor) else np.asarray(depth_mm)
+    if d.dtype != np.uint16 or d.ndim != 3 or d.shape[1] != d.shape[2]:
+        raise ValueError("depth_mm must be (B,R,R) uint16")
+    d = np.ascontiguousarray(d)
+    B, R = d.shape[0], d.shape[1]
+    c = np.ascontiguousarray(center.cpu().numpy() if isinstance(center, torch.Tensor) else center, dtype=np.float32)
+    q = np.ascontiguousarray(cube.cpu().numpy() if isinstance(cube, torch.Tensor) else cube, dtype=np.float32)
+    rows = np.empty((B, R, 2), np.uint16)
+    off = np.empty(B + 1, np.uint32)
+    payload = np.empty(B * R * R, np.uint16)
+    n = lib.dsf_pack_u16_rows(B, R, d.ctypes.data, c.ctypes.data, q.ctypes.data, int(invalid_value), rows.ctypes.data,
+                              off.ctypes.data, payload.ctypes.data, payload.size)
+    if n < 0:
+        raise RuntimeError("dsf_pack_u16_rows failed (bad arguments)")
+    t_rows = torch.from_numpy(rows)
+    t_off = torch.from_numpy(off.view(np.int32))
+    t_pay = torch.from_numpy(payload[:max(int(n), 1)].copy())
+    if pin and torch.cuda.is_available():
+        t_rows, t_off, t_pay = t_rows.pin_memory(), t_off.pin_memory(), t_pay.pin_memory()
+    return RowRunTarget(t_rows, t_off, t_pay, R)
+
+
+def target_from_u16_rows(packed, center, cube, invalid_value=0, out=None, buffers=None):
+    """RowRunTarget (host) -> normalised fp32 target (B,R,R) on the device: three small H2D copies + one kernel.
+    ``buffers`` = optional persistent device tensors (rows, hand_offset, payload) to copy into."""
+    lib = L.lib()
+    center, cube = L.f32c(center), L.f32c(cube)
+    dev = center.device
+    B, R = packed.batch, packed.R
+    if buffers is None:
+        buffers = (torch.empty(B, R, 2, dtype=torch.uint16, device=dev), torch.empty(B + 1, dtype=torch.int32, device=dev),
+                   torch.empty(B * R * R, dtype=torch.uint16, device=dev))
+    d_rows, d_off, d_pay = buffers
+    n = packed.payload.numel()
+    d_rows.copy_(packed.rows, non_blocking=True)
+    d_off.copy_(packed.hand_offset, non_blocking=True)
+    d_pay[:n].copy_(packed.payload, non_blocking=True)
+    if out is None:
+        out = torch.empty(B, R, R, dtype=torch.float32, device=dev)
+    L.check(lib.dsf_target_from_u16_rows(B, R, d_rows.data_ptr(), d_off.data_ptr(), d_pay.data_ptr(), center.data_ptr(),
+                                         cube.data_ptr(), int(invalid_value), out.data_ptr(), L.stream_ptr()))
+    return out

@@ -330,6 +330,20 @@ int dsf_uvd_img_to_xyz(int batch, int R, const float* img, const float* center3d
 int dsf_target_from_u16(int batch, int R, const unsigned short* depth_mm, const float* center3d,
                         const float* cube, int invalid_value, float* target, dsfStream_t stream);
 
+/* Row-run transport of the same crop (about 80 % of a hand crop is background): per row only the span from the
+ * first to the last non-background pixel travels.  rows (B,R,2) uint16 = (first column, length), hand_offset (B+1)
+ * uint32 = start of each hand's pixels in the packed uint16 payload.  dsf_target_from_u16_rows rebuilds the
+ * normalised fp32 target on the device, bit-identical to dsf_target_from_u16 of the unpacked crop (R <= 512).
+ * dsf_pack_u16_rows is the loader's side (plain host code, no device): it fills rows / hand_offset / payload from
+ * (B,R,R) uint16 crops and returns the number of payload pixels (-1: capacity too small).  Background = depth 0,
+ * the invalid marker, or a value at / beyond the far plane center_z + cube_z / 2. */
+int dsf_target_from_u16_rows(int batch, int R, const unsigned short* rows, const unsigned int* hand_offset,
+                             const unsigned short* payload, const float* center3d, const float* cube,
+                             int invalid_value, float* target, dsfStream_t stream);
+long dsf_pack_u16_rows(int batch, int R, const unsigned short* depth_mm, const float* center3d, const float* cube,
+                       int invalid_value, unsigned short* rows, unsigned int* hand_offset, unsigned short* payload,
+                       long payload_cap);
+
 /* I1 - replaces eval_coll.py:611-626 self_intersection (with get_part_mesh :348-373) and
  * util/intersect.py:102-107 intersect_vox, i.e. trimesh's voxelized(pitch).points +
  * mesh.contains(points) on the CPU.  verts (B,n_verts,3) fp32 (mm); cap centre c = mean of the

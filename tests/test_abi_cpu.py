@@ -56,3 +56,46 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "liboracle" not in src, f
+
+
+def test_row_run_packer_round_trip_cpu():
+    """dsf_pack_u16_rows is host code (the loader's side of the row-run transport): its output must reproduce the
+    crop wherever the crop is not background, and describe every row by one span."""
+    import numpy as np
+    import torch
+
+    from dsf_b200.pcl import pack_target_rows
+
+    rng = np.random.RandomState(0)
+    B, R = 5, 64
+    d = np.zeros((B, R, R), np.uint16)
+    center = np.tile(np.array([[0.0, 0.0, 800.0]], np.float32), (B, 1))
+    cube = np.full((B, 3), 250.0, np.float32)
+    for b in range(B - 1):                                   # blobs of valid depth, holes inside, far-plane pixels
+        r0, c0 = rng.randint(5, 30, 2)
+        blob = rng.randint(700, 1000, (25, 20)).astype(np.uint16)
+        blob[rng.rand(25, 20) < 0.2] = 0
+        d[b, r0:r0 + 25, c0:c0 + 20] = blob
+    d[0, 10, :] = 0                                          # an empty row inside the blob; hand B-1 is all background
+    d[1, 12, 3] = 60000                                      # beyond the far plane: background
+    p = pack_target_rows(torch.from_numpy(d), torch.from_numpy(center), torch.from_numpy(cube), pin=False)
+    rows, off, pay = p.rows.numpy(), p.hand_offset.numpy(), p.payload.numpy()
+    far = (center[:, 2] + cube[:, 2] / np.float32(2)).astype(np.float32)
+    fg = (d != 0) & (d.astype(np.float32) < far[:, None, None])
+    rebuilt = np.zeros_like(d)
+    n = 0
+    for b in range(B):
+        assert off[b] == n
+        for r in range(R):
+            c0, ln = rows[b, r]
+            cols = np.nonzero(fg[b, r])[0]
+            if len(cols) == 0:
+                assert ln == 0
+                continue
+            assert c0 == cols[0] and ln == cols[-1] - cols[0] + 1
+            rebuilt[b, r, c0:c0 + ln] = pay[n:n + ln]
+            n += ln
+    assert off[B] == n and (n == len(pay) or (n == 0 and len(pay) == 1))
+    assert np.array_equal(rebuilt[fg], d[fg])
+    assert rows[B - 1, :, 1].sum() == 0 and rows[0, 10, 1] == 0
+    assert p.nbytes < d.nbytes / 2
