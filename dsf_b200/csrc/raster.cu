@@ -427,7 +427,7 @@ static size_t raster_fwd_smem(int R, int F) {
 // exact evaluation of pixel (i,j) against face f, commit to the z-buffer
 template <bool PERSP>
 __device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned int f, int i, int j, int tx0,
-                                                int ty0, bool zmin_bounds) {
+                                                int ty0, bool zmin_bounds, bool bbox_check) {
     const unsigned int pk = s.fp[f];
     const int a0 = pk & 1023, a1 = (pk >> 10) & 1023, a2 = pk >> 20;
     const float z0 = s.vn[3 * a0 + 2], z1 = s.vn[3 * a1 + 2], z2 = s.vn[3 * a2 + 2];
@@ -442,6 +442,9 @@ __device__ __forceinline__ void eval_and_commit(const RasterSmem& s, unsigned in
     const float x1 = s.vn[3 * a1], y1 = s.vn[3 * a1 + 1];
     const float x2 = s.vn[3 * a2], y2 = s.vn[3 * a2 + 1];
     const float px = s.xs[i], py = s.ys[j];
+    // the oracle's bounding-box rejection, exact (the candidate ranges of the direct raster are supersets)
+    if (bbox_check && (px > fmaxf(x0, fmaxf(x1, x2)) || px < fminf(x0, fminf(x1, x2)) ||
+                       py > fmaxf(y0, fmaxf(y1, y2)) || py < fminf(y0, fminf(y1, y2)))) return;
     const float area = __fadd_rn(edge_rn(x2, y2, x0, y0, x1, y1), EPS);
     const float e0 = edge_rn(px, py, x1, y1, x2, y2);
     const float e1 = edge_rn(px, py, x2, y2, x0, y0);
@@ -597,7 +600,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         for (int c = lane; c < n_cands; c += 32) {
             const unsigned int e = my_cands[c];
             eval_and_commit<PERSP>(s, e & 2047u, tx0 + (int)((e >> 18) & 127u), ty0 + (int)((e >> 11) & 127u), tx0, ty0,
-                                   (e >> 25) & 1u);
+                                   (e >> 25) & 1u, vw.affine);
         }
         n_cands = 0;
         __syncwarp();
@@ -629,11 +632,22 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                 if (PERSP || farea < 0.f || farea > 2e-4f) e_flags |= 256u;      // eps / A < 5e-5
                 const float xmin = fminf(x0, fminf(x1, x2)), xmax = fmaxf(x0, fmaxf(x1, x2));
                 const float ymin = fminf(y0, fminf(y1, y2)), ymax = fmaxf(y0, fmaxf(y1, y2));
-                ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
-                jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
-                if (ja <= jb) {
-                    ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
-                    ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
+                if (vw.affine) {
+                    // direct raster: index = a * ndc + b exactly, so the bbox maps to index ranges in closed form; a
+                    // thousandth of a pixel of slack makes them supersets, the exact bbox comparison of the oracle is
+                    // repeated per candidate (eval_and_commit)
+                    const float lim = 1e6f;
+                    ja = max(cy0, (int)ceilf(fminf(fmaxf(fmaf(vw.ay, ymax, vw.by) - 1e-3f, -lim), lim)));
+                    jb = min(cy1, (int)floorf(fminf(fmaxf(fmaf(vw.ay, ymin, vw.by) + 1e-3f, -lim), lim)));
+                    ia = max(cx0, (int)ceilf(fminf(fmaxf(fmaf(vw.ax, xmax, vw.bx) - 1e-3f, -lim), lim)));
+                    ib = min(cx1, (int)floorf(fminf(fmaxf(fmaf(vw.ax, xmin, vw.bx) + 1e-3f, -lim), lim)));
+                } else {
+                    ja = max(cy0, first_le(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymax));
+                    jb = min(cy1, last_ge(s.ys, vw.ylo, vw.yhi, vw.ay, vw.by, ymin));
+                    if (ja <= jb) {
+                        ia = max(cx0, first_le(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmax));
+                        ib = min(cx1, last_ge(s.xs, vw.xlo, vw.xhi, vw.ax, vw.bx, xmin));
+                    }
                 }
                 if (ia <= ib && ja <= jb && fabsf(farea) >= 1e-5f) {     // slivers keep the whole bbox row
                     // edge i of the oracle: e_i(px) = (px - xa) * dy - (py - ya) * dx, crossing at
@@ -708,13 +722,16 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             int slot = warp_excl_scan(len, lane, &c_total);
             if (n_cands + c_total > RT_WCANDS) flush_cands();
             if (c_total > RT_WCANDS) {                           // very large faces: evaluate in place
-                for (int k = ka; k <= kb; ++k) eval_and_commit<PERSP>(s, fi, k, j, tx0, ty0, (o_fl >> 8) & 1u);
+                for (int k = ka; k <= kb; ++k) eval_and_commit<PERSP>(s, fi, k, j, tx0, ty0, (o_fl >> 8) & 1u, vw.affine);
                 __syncwarp();
                 continue;
             }
             slot += n_cands;
             const unsigned int base = fi | ((unsigned int)(j - ty0) << 11) | ((o_fl & 256u) << 17);
-            for (int k = ka; k <= kb; ++k) my_cands[slot++] = base | ((unsigned int)(k - tx0) << 18);
+            // runs are mostly one or two pixels long: the first two stores are straight-line code
+            if (len > 0) my_cands[slot] = base | ((unsigned int)(ka - tx0) << 18);
+            if (len > 1) my_cands[slot + 1] = base | ((unsigned int)(ka + 1 - tx0) << 18);
+            for (int k = ka + 2; k <= kb; ++k) my_cands[slot + (k - ka)] = base | ((unsigned int)(k - tx0) << 18);
             n_cands += c_total;
         }
     }
