@@ -53,6 +53,8 @@ struct DsfMano {
     int* wj_ptr;   // (17) CSR of the skin weights, joint-major
     int* wj_idx;
     float* wj_w;
+    int* wv_ptr;   // (779) CSR of the skin weights, vertex-major (a vertex follows a handful of joints, not 16)
+    int2* wv_ent;  // (nnz) {joint, float bits of the weight}
     int* faces;    // (n_faces,3)
     unsigned int* faces_packed;   // (n_faces) i0 | i1 << 10 | i2 << 20
     unsigned short* face_order;   // (n_faces) face ids, largest rest-pose area first
@@ -106,6 +108,32 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Sum 16 per-lane values over the warp with 16 shuffles instead of 80: at every butterfly step a lane hands
+// over the half of its values the partner will own and keeps the other half.  Returns the total of value
+// (lane >> 1) (every total lands on a pair of lanes); deterministic order.
+__device__ __forceinline__ float warp_sum16_scatter(const float* v, int lane) {
+    float a[8], b[4], c[2];
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = h4 ? v[8 + i] : v[i], give = h4 ? v[i] : v[8 + i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = h3 ? a[4 + i] : a[i], give = h3 ? a[i] : a[4 + i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = h2 ? b[2 + i] : b[i], give = h2 ? b[i] : b[2 + i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+    const float keep = h1 ? c[1] : c[0], give = h1 ? c[0] : c[1];
+    const float d = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
 }
 
 // y = M(3x3 row-major) * x

@@ -147,6 +147,21 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
         wptr[j + 1] = (int)widx.size();
     }
     if (widx.empty()) { widx.push_back(0); wval.push_back(0.f); }
+    // ... and vertex-major, for the skinning loops
+    std::vector<int> vptr(NV + 1, 0);
+    std::vector<int2> vent;
+    for (int v = 0; v < NV; ++v) {
+        for (int j = 0; j < NJ; ++j) {
+            const float x = host->weights[v * NJ + j];
+            if (x != 0.f) {
+                int bits;
+                memcpy(&bits, &x, 4);
+                vent.push_back(make_int2(j, bits));
+            }
+        }
+        vptr[v + 1] = (int)vent.size();
+    }
+    if (vent.empty()) vent.push_back(make_int2(0, 0));
     std::vector<float> mask(DSF_NSPHERE * DSF_NSPHERE);
     dsf_build_collision_mask(mask.data());
 
@@ -167,6 +182,8 @@ extern "C" int dsf_mano_create(const DsfManoHost* host, DsfMano** out) {
     rc |= upload(&h->wj_ptr, wptr.data(), wptr.size());
     rc |= upload(&h->wj_idx, widx.data(), widx.size());
     rc |= upload(&h->wj_w, wval.data(), wval.size());
+    rc |= upload(&h->wv_ptr, vptr.data(), vptr.size());
+    rc |= upload(&h->wv_ent, vent.data(), vent.size());
     rc |= upload(&h->faces, host->faces, (size_t)host->n_faces * 3);
     std::vector<unsigned int> fpk((host->n_faces + 3) & ~3, 0u);     // padded to 16 bytes for bulk copies
     for (int f = 0; f < host->n_faces; ++f)
@@ -222,7 +239,7 @@ extern "C" int dsf_mano_free(DsfMano* h) {
     if (!h) return DSF_OK;
     void* ptrs[] = {h->BTh, h->BTl, h->Bh, h->Bl, h->vt, h->W, h->comp, h->mean, h->Jt, h->JS,
                     h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx, h->wj_w, h->faces, h->faces_packed,
-                    h->face_order, h->coll_mask, h->vf_ptr, h->vf_ent};
+                    h->face_order, h->coll_mask, h->vf_ptr, h->vf_ent, h->wv_ptr, h->wv_ent};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free(h);
@@ -384,7 +401,7 @@ static int ensure_constants() {
 }
 
 __global__ void __launch_bounds__(SKIN_T)
-mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ W,
+mano_skin_kernel(int B, const float* __restrict__ ws, const int* __restrict__ wv_ptr, const int2* __restrict__ wv_ent,
                  const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
                  const float* __restrict__ jr_w, const float* __restrict__ cam, int ld_cam, float unit_scale,
                  float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ Rs) {
@@ -416,19 +433,13 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ 
         float T[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
-        const float4* wp = reinterpret_cast<const float4*>(W + v * NJ);
+        const int e1 = __ldg(wv_ptr + v + 1);
+        for (int k = __ldg(wv_ptr + v); k < e1; ++k) {           // the joints this vertex follows, ascending
+            const int2 en = __ldg(wv_ent + k);
+            const float wgt = __int_as_float(en.y);
+            const float* Aj = sA[en.x];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 w4 = __ldg(wp + q);
-            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (wv[i] != 0.f) {
-                    const float* Aj = sA[q * 4 + i];
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) T[e] = fmaf(wv[i], Aj[e], T[e]);
-                }
-            }
+            for (int e = 0; e < 12; ++e) T[e] = fmaf(wgt, Aj[e], T[e]);
         }
         float ox = T[0] * x + T[1] * y + T[2] * z + T[9];
         float oy = T[3] * x + T[4] * y + T[5] * z + T[10];
@@ -473,7 +484,7 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const float* __restrict__ 
 #define SKB_T 256
 
 __global__ void __launch_bounds__(SKB_T)
-mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
+mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_ptr, const int2* __restrict__ wv_ent,
                      const int* __restrict__ jr_ptr, const int* __restrict__ jr_idx,
                      const float* __restrict__ jr_w, const int* __restrict__ wj_ptr,
                      const int* __restrict__ wj_idx, const float* __restrict__ wj_w,
@@ -506,6 +517,13 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
     // vertex cotangent straight from the rasteriser's per-tile shares (fused step): sum the tiles, apply the
     // hand's loss normalisation gk / zhalf
     const float gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
+    // the flagged tiles of this hand, resolved once (at most 8 tiles are walked through registers; more fall back)
+    const float* tile_ptr[8];
+    int n_live_tiles = 0;
+    if (gt.gv_tile && gt.n_tiles <= 8)
+        for (int t = 0; t < gt.n_tiles; ++t)
+            if (gt.gv_flag[(size_t)hand * gt.n_tiles + t])
+                tile_ptr[n_live_tiles++] = gt.gv_tile + ((size_t)hand * gt.n_tiles + t) * NVW * 3;
     if (lf.parts && lf.n_mesh == B && tid == 0) {            // per-hand loss record = sum of its tiles
         float a = 0.f, c = 0.f;
         for (int t = 0; t < lf.n_tiles; ++t) {
@@ -517,9 +535,17 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
     for (int v = tid; v < NVW; v += SKB_T) {
         float a = gv ? gv[3 * v] : 0.f, b = gv ? gv[3 * v + 1] : 0.f, c = gv ? gv[3 * v + 2] : 0.f;
         if (gt.gv_tile) {
-            a = gts * grad_tiles_load(gt, hand, 3 * v);
-            b = gts * grad_tiles_load(gt, hand, 3 * v + 1);
-            c = gts * grad_tiles_load(gt, hand, 3 * v + 2);
+            if (gt.n_tiles <= 8) {
+                a = b = c = 0.f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < n_live_tiles) { a += tile_ptr[t][3 * v]; b += tile_ptr[t][3 * v + 1]; c += tile_ptr[t][3 * v + 2]; }
+                a *= gts; b *= gts; c *= gts;
+            } else {
+                a = gts * grad_tiles_load(gt, hand, 3 * v);
+                b = gts * grad_tiles_load(gt, hand, 3 * v + 1);
+                c = gts * grad_tiles_load(gt, hand, 3 * v + 2);
+            }
         }
         sg[3 * v] = a; sg[3 * v + 1] = b; sg[3 * v + 2] = c;
         pt[1] += a; pt[2] += b; pt[3] += c;
@@ -570,18 +596,12 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
-        const float4* wp = reinterpret_cast<const float4*>(W + v * NJ);
+        const int e1 = __ldg(wv_ptr + v + 1);
+        for (int k = __ldg(wv_ptr + v); k < e1; ++k) {
+            const int2 en = __ldg(wv_ent + k);
+            const float wgt = __int_as_float(en.y);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 w4 = __ldg(wp + q);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (wv[i] != 0.f) {
-#pragma unroll
-                    for (int e = 0; e < 9; ++e) T[e] = fmaf(wv[i], sGr[q * 4 + i][e], T[e]);
-                }
-            }
+            for (int e = 0; e < 9; ++e) T[e] = fmaf(wgt, sGr[en.x][e], T[e]);
         }
         GVP[3 * v] = T[0] * g0 + T[3] * g1 + T[6] * g2;
         GVP[3 * v + 1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
@@ -593,9 +613,9 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
     // joint walks that joint's weight list (CSR) and reduces with shuffles
     float* GA = wsh + WS_GA;
     for (int j = warp; j < NJ; j += SKB_T / 32) {
-        float acc[12];
+        float acc[16];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
         for (int e = wj_ptr[j] + lane; e < wj_ptr[j + 1]; e += 32) {
             const int v = wj_idx[e];
             const float w = wj_w[e];
@@ -608,12 +628,9 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const float* __restrict__ W,
                 acc[9 + r] += wg;
             }
         }
-#pragma unroll
-        for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
-        if (lane == 0) {
-#pragma unroll
-            for (int e = 0; e < 12; ++e) GA[j * 12 + e] = acc[e];
-        }
+        // 12 warp sums as one scatter-reduction: total e lands on lanes 2e, 2e + 1
+        const float tot = warp_sum16_scatter(acc, lane);
+        if (!(lane & 1) && (lane >> 1) < 12) GA[j * 12 + (lane >> 1)] = tot;
     }
     // camera gradient
     if (g_cam) {
@@ -803,7 +820,7 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
     // v_posed = v_template + [beta | Rs - I] . [shapedirs ; posedirs]
     rc = dsf_blend_forward_gemm(B, ws + WS_X, WS_PER_HAND, h->BTh, h->BTl, ws + WS_VP, WS_PER_HAND, h->vt, st);
     if (rc) return rc;
-    mano_skin_kernel<<<B, SKIN_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
+    mano_skin_kernel<<<B, SKIN_T, 0, st>>>(B, ws, h->wv_ptr, h->wv_ent, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
                                            unit_scale, verts, joints, Rs);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
@@ -816,7 +833,7 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
     int rc = ensure_constants();
     if (rc) return rc;
     ChainTopo topo = topo_of(h);
-    mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->W, h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx,
+    mano_skin_bwd_kernel<<<B, SKB_T, 0, st>>>(B, ws, h->wv_ptr, h->wv_ent, h->jr_ptr, h->jr_idx, h->jr_w, h->wj_ptr, h->wj_idx,
                                               h->wj_w, p->cam, p->ld_cam,
                                               unit_scale, verts, joints, g_verts, g_joints,
                                               p->cam ? g->cam : nullptr, g->ld_cam, gt ? *gt : GradTiles{}, cube,
