@@ -27,13 +27,15 @@
 #define VIEW DSF_VIEW_STRIDE
 
 // workspace layout (floats per hand)
-#define WS_X 0
-#define WS_VP (WS_X + KP)
+#define WS_X 0                            // GEMM operand [beta | Rs - I | 0], split into tf32 hi (BLEND_KPAD) and lo (BLEND_KPAD)
+#define WS_VP (WS_X + 2 * BLEND_KPAD)
 #define WS_RJ (WS_VP + NP)
 #define WS_GVP (WS_RJ + NJ * RJ_STRIDE)
 #define WS_GA (WS_GVP + NP)
 #define WS_GX (WS_GA + NJ * 12)          // BLEND_SPLITS split-K partials of g_X, KP floats each
 #define WS_PER_HAND (WS_GX + BLEND_SPLITS * KP)
+// the MANO scratch holds whole groups of 8 hands (the tensor maps of the blend GEMM address rows in groups of 8)
+#define WS_HANDS(b) (((long)(b) + 7) & ~7L)
 
 struct DsfMano {
     float* BTh;    // (BLEND_NPAD, BLEND_KPAD) basis^T, tf32 hi part, zero padded   (forward B operand)

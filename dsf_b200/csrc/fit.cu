@@ -9,11 +9,11 @@
 // workspace of one fused step (floats): MANO scratch | per-tile loss sums | per-tile gradient flags |
 // per-tile vertex-gradient shares (the first NVW*3 floats per hand double as g_verts of the unfused path) |
 // the rasteriser's done-counter
-static inline size_t fit_ws_parts(int n_mesh_mano) { return (size_t)n_mesh_mano * WS_PER_HAND; }
+static inline size_t fit_ws_parts(int n_mesh_mano) { return (size_t)WS_HANDS(n_mesh_mano) * WS_PER_HAND; }
 
 extern "C" long dsf_fit_workspace_floats(int batch, int R) {
     const long nt = dsf_raster_tiles(R);
-    return (long)batch * (WS_PER_HAND + 2L * nt + nt + nt * NVW * 3) + 4;
+    return WS_HANDS(batch) * WS_PER_HAND + (long)batch * (2L * nt + nt + nt * NVW * 3) + 4;
 }
 
 extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
@@ -229,7 +229,7 @@ static void render_params(const float* params, int ld, int quat_dim, float* g_pa
 }
 
 extern "C" long dsf_render_workspace_floats(int batch) {
-    return (long)batch * (WS_PER_HAND + NVW * 3 + NJOUT * 3);
+    return WS_HANDS(batch) * WS_PER_HAND + (long)batch * (NVW * 3 + NJOUT * 3);
 }
 
 extern "C" int dsf_render_forward(const DsfMano* h, int batch, int R, const float* params, int ld_params, int quat_dim,
@@ -272,7 +272,7 @@ extern "C" int dsf_render_backward(const DsfMano* h, int batch, int R, const flo
     DSF_REQUIRE(batch > 0 && batch <= 65535, "batch must be in [1,65535] per call");
     DSF_REQUIRE((quat_dim == 3 || quat_dim == 4) && ld_params >= quat_dim + 59, "params must be (B, 62 | 63)");
     cudaStream_t st = (cudaStream_t)stream;
-    float* g_verts = workspace + (size_t)batch * WS_PER_HAND;
+    float* g_verts = workspace + (size_t)WS_HANDS(batch) * WS_PER_HAND;
     float* g_joints = g_verts + (size_t)batch * NVW * 3;
     DsfManoParams p;
     DsfManoGrads g;
@@ -354,7 +354,7 @@ views_place_bwd_kernel(int views, const float* __restrict__ g_cam, GradTiles gt,
 extern "C" long dsf_fit_views_workspace_floats(int batch, int views, int R) {
     const long nm = (long)batch * views, nt = dsf_raster_tiles(R);
     const long grad = nt * NVW * 3 > NVW * 3 ? nt * NVW * 3 : NVW * 3;
-    return (long)batch * (WS_PER_HAND + NVW * 3) + nm * ((long)NVW * 3 + grad + 3L * nt) + 4;
+    return WS_HANDS(batch) * WS_PER_HAND + (long)batch * NVW * 3 + nm * ((long)NVW * 3 + grad + 3L * nt) + 4;
 }
 
 extern "C" int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R, const float* params,
@@ -374,7 +374,7 @@ extern "C" int dsf_fit_step_views(const DsfMano* h, int batch, int views, int R,
     const int nm = batch * views, n_tiles = dsf_raster_tiles(R);
     const size_t grad = (size_t)(n_tiles > 1 ? n_tiles : 1) * NVW * 3;
     float* ws_mano = workspace;
-    float* g_verts = workspace + (size_t)batch * WS_PER_HAND;
+    float* g_verts = workspace + (size_t)WS_HANDS(batch) * WS_PER_HAND;
     float* verts_cam = g_verts + (size_t)batch * NVW * 3;
     float* g_cam = verts_cam + (size_t)nm * NVW * 3;              // dense cotangent, or the per-tile shares
     float* parts_tile = g_cam + (size_t)nm * grad;

@@ -246,7 +246,7 @@ extern "C" int dsf_mano_free(DsfMano* h) {
     return DSF_OK;
 }
 
-extern "C" long dsf_mano_workspace_floats(int batch) { return (long)batch * WS_PER_HAND; }
+extern "C" long dsf_mano_workspace_floats(int batch) { return WS_HANDS(batch) * WS_PER_HAND; }
 extern "C" const int* dsf_mano_faces_device(const DsfMano* h, int* n_faces) {
     if (!h) return nullptr;
     if (n_faces) *n_faces = h->n_faces;
@@ -321,14 +321,21 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     }
     float* wsh = ws + (size_t)hh * WS_PER_HAND;
     if (live) {
-        // GEMM operand row X = [beta | Rs - I | 0]
-        float* X = wsh + WS_X;
-        if (j < 10) X[j] = s_beta[hl][j];
+        // GEMM operand row X = [beta | Rs - I | 0], written already split for the 3xTF32 tensor-core GEMM:
+        // hi = the value with the low 13 mantissa bits cleared (exact in tf32), lo = the remainder
+        float* Xh = wsh + WS_X;
+        float* Xl = Xh + BLEND_KPAD;
+        auto put = [&](int k, float v) {
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            Xh[k] = hi;
+            Xl[k] = v - hi;
+        };
+        if (j < 10) put(j, s_beta[hl][j]);
         if (j >= 1) {
 #pragma unroll
-            for (int e = 0; e < 9; ++e) X[10 + 9 * (j - 1) + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+            for (int e = 0; e < 9; ++e) put(10 + 9 * (j - 1) + e, R[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f));
         }
-        if (j < KP - 145) X[145 + j] = 0.f;
+        if (j < BLEND_KPAD - 145) { Xh[145 + j] = 0.f; Xl[145 + j] = 0.f; }
     }
 
     float Gr[9], Gt[3];
@@ -374,8 +381,8 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
 }
 
 // K2: the blend-shape contraction runs on the tensor cores, see blend_gemm.cu
-int dsf_blend_forward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
-                           const float* bias, cudaStream_t st);
+int dsf_blend_forward_gemm(int M, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, float* C,
+                           int ldc, const float* bias, cudaStream_t st);
 int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
                             long split_stride, cudaStream_t st);
 int dsf_blend_backward_splits(int M);
@@ -818,7 +825,8 @@ int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float
                                                                               h->JS, topo, ws);
     DSF_CHECK_LAUNCH();
     // v_posed = v_template + [beta | Rs - I] . [shapedirs ; posedirs]
-    rc = dsf_blend_forward_gemm(B, ws + WS_X, WS_PER_HAND, h->BTh, h->BTl, ws + WS_VP, WS_PER_HAND, h->vt, st);
+    rc = dsf_blend_forward_gemm(B, ws + WS_X, ws + WS_X + BLEND_KPAD, WS_PER_HAND, h->BTh, h->BTl, ws + WS_VP,
+                                WS_PER_HAND, h->vt, st);
     if (rc) return rc;
     mano_skin_kernel<<<B, SKIN_T, 0, st>>>(B, ws, h->wv_ptr, h->wv_ent, h->jr_ptr, h->jr_idx, h->jr_w, p->cam, p->ld_cam,
                                            unit_scale, verts, joints, Rs);

@@ -264,7 +264,7 @@ class MultiViewFitStep:
     def verts_cam(self):
         """(B*V,779,3) camera-space vertices of every view, as the last step left them in the workspace
         (layout of dsf_fit_step_views: MANO scratch | g_verts | verts_cam | ...)."""
-        off = self.B * (self.lib.dsf_mano_workspace_floats(1) + L.NVW * 3)
+        off = self.lib.dsf_mano_workspace_floats(self.B) + self.B * L.NVW * 3
         n = self.B * self.V * L.NVW * 3
         return self.ws[off:off + n].view(self.B * self.V, L.NVW, 3)
 
