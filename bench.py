@@ -528,22 +528,23 @@ def run_ours(args):
         # the same launch, flops per pair as documented at dsf_point_face_stats
         from dsf_b200 import _lib as _L
         nF = int(layer.faces_int.shape[0])
-        st3 = torch.zeros(3, dtype=torch.int64, device=dev)
+        st3 = torch.zeros(4, dtype=torch.int64, device=dev)
         dd = torch.empty(b4, P, device=dev)
         ii = torch.empty(b4, P, dtype=torch.int32, device=dev)
-        oo = torch.empty(b4, P, dtype=torch.int32, device=dev)
+        oo = torch.empty(b4 * (P + nF), dtype=torch.int32, device=dev)
         vv = v4.detach().contiguous()
         _L.check(_L.lib().dsf_point_face_stats(b4, P, vv.shape[1], nF, pcl.data_ptr(), vv.data_ptr(),
                                                layer.faces_int.data_ptr(), dd.data_ptr(), ii.data_ptr(), oo.data_ptr(),
                                                st3.data_ptr(), _L.stream_ptr()))
-        n_cull, n_in, n_edge = (int(x) for x in st3.tolist())
+        n_cull, n_in, n_edge, n_grp = (int(x) for x in st3.tolist())
         pairs = b4 * P * nF
-        flops = 16 * n_cull + 56 * n_in + 120 * n_edge
+        flops = 16 * (n_cull + n_grp) + 56 * n_in + 120 * n_edge
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         other["C4_icp_batch1024"] = {
             "hands": b4, "points": P, "faces": nF, "ms_fwd_bwd": t_icp, "ms_fwd": t_icp_fwd,
             "point_triangle_tests_per_s": pairs / (t_icp * 1e-3),
-            "pairs": {"all": pairs, "sphere_culled": n_cull, "evaluated_interior": n_in, "evaluated_edge": n_edge,
+            "pairs": {"all": pairs, "group_sphere_tests": n_grp, "culled_with_their_group": pairs - n_cull - n_in - n_edge,
+                      "sphere_culled": n_cull, "evaluated_interior": n_in, "evaluated_edge": n_edge,
                       "evaluated_frac": (n_in + n_edge) / pairs},
             "roofline": {"bound": "fp32", "kernel": "point_face_fwd_kernel", "achieved": flops / (t_icp_fwd * 1e-3) / 1e12,
                          "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / (t_icp_fwd * 1e-3) / 1e12 / fp32_peak,
@@ -552,7 +553,7 @@ def run_ours(args):
                          "peak_source": "148 SMs x 128 FP32 lanes x 2 (FMA) x 1.965 GHz; ms_fwd includes the point "
                                         "sort launch (< 3 % of it)",
                          "brute_force_equivalent": pairs * 120 / (t_icp_fwd * 1e-3) / 1e12},
-            "note": "ICPLoss fwd+bwd; exhaustive scan with a per-face bounding-sphere cull over spatially ordered points; "
+            "note": "ICPLoss fwd+bwd; exhaustive scan with group (8 faces) and per-face bounding-sphere culls over spatially ordered points and faces; "
                     "FP32 compute bound, bytes negligible"}
         other["C4_coll_batch1024"] = {"hands": b4, "ms_fwd_bwd": t_coll, "hands_per_s": b4 / (t_coll * 1e-3),
                                       "note": "latency bound: one warp per hand, 9.6 KB in per hand = %.0f GB/s"

@@ -187,14 +187,85 @@ point_sort_kernel(int P, const float* __restrict__ points, int* __restrict__ ord
     for (int i = tid; i < P; i += PS_THREADS) order[(size_t)b * P + atomicAdd(&s_hist[cell(i)], 1)] = i;
 }
 
+// Companion pre-pass: order the FACES of each hand the same way (Morton cell of the centroid in the mesh's own
+// bounding box), so that consecutive faces are neighbours in space and groups of PF_GROUP of them fit a small
+// common bounding sphere: the scan below then rejects whole groups with one test.  face_order (B,F) int32.
+__global__ void __launch_bounds__(PS_THREADS)
+face_sort_kernel(int V, int F, const float* __restrict__ verts, const int* __restrict__ faces, int* __restrict__ order) {
+    __shared__ int s_hist[PS_GRID * PS_GRID * PS_GRID];
+    __shared__ float s_red[PS_THREADS / 32][6];
+    __shared__ int s_warp[PS_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* vb = verts + (size_t)b * V * 3;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < V; i += PS_THREADS)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], vb[3 * i + k]); hi[k] = fmaxf(hi[k], vb[3 * i + k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s_red[warp][k] = lo[k]; s_red[warp][3 + k] = hi[k]; }
+    for (int i = tid; i < PS_GRID * PS_GRID * PS_GRID; i += PS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    float inv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int w = 0; w < PS_THREADS / 32; ++w) { lo[k] = fminf(lo[k], s_red[w][k]); hi[k] = fmaxf(hi[k], s_red[w][3 + k]); }
+        inv[k] = hi[k] > lo[k] ? (float)PS_GRID / (hi[k] - lo[k]) : 0.f;
+    }
+    auto cell = [&](int f) {
+        const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+        int c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float m = (vb[3 * i0 + k] + vb[3 * i1 + k] + vb[3 * i2 + k]) * (1.f / 3.f);
+            const int q = (int)((m - lo[k]) * inv[k]);
+            c[k] = q < 0 ? 0 : (q > PS_GRID - 1 ? PS_GRID - 1 : q);
+        }
+        int key = 0;
+#pragma unroll
+        for (int bit = 0; bit < 4; ++bit)
+            key |= (((c[0] >> bit) & 1) << (3 * bit)) | (((c[1] >> bit) & 1) << (3 * bit + 1)) |
+                   (((c[2] >> bit) & 1) << (3 * bit + 2));
+        return key;
+    };
+    for (int f = tid; f < F; f += PS_THREADS) atomicAdd(&s_hist[cell(f)], 1);
+    __syncthreads();
+    const int per = PS_GRID * PS_GRID * PS_GRID / PS_THREADS, b0 = tid * per;
+    int local = 0;
+    for (int i = 0; i < per; ++i) local += s_hist[b0 + i];
+    int incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int run = incl - local;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    for (int i = 0; i < per; ++i) { const int h = s_hist[b0 + i]; s_hist[b0 + i] = run; run += h; }
+    __syncthreads();
+    for (int f = tid; f < F; f += PS_THREADS) order[(size_t)b * F + atomicAdd(&s_hist[cell(f)], 1)] = f;
+}
+
+#define PF_GROUP 8       // faces per group sphere (PF_CHUNK is a multiple)
+
 // STATS: the same scan, additionally counting per category how many (point, face) pairs were only sphere-tested,
 // evaluated on the interior branch, and evaluated on the edge branch (bench.py's FP32 roofline of config C4)
 template <bool STATS>
 __global__ void __launch_bounds__(PF_THREADS)
 point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, const float* __restrict__ verts,
-                      const int* __restrict__ faces, const int* __restrict__ order, float* __restrict__ dists,
-                      int* __restrict__ idxs, unsigned long long* __restrict__ stats) {
-    unsigned int n_cull = 0, n_in = 0, n_edge = 0;
+                      const int* __restrict__ faces, const int* __restrict__ order, const int* __restrict__ face_order,
+                      float* __restrict__ dists, int* __restrict__ idxs, unsigned long long* __restrict__ stats) {
+    unsigned int n_cull = 0, n_in = 0, n_edge = 0, n_grp = 0;
+    __shared__ float4 s_grp[PF_CHUNK / PF_GROUP];       // bounding sphere of each group of PF_GROUP staged faces
+    __shared__ unsigned short s_fid[PF_CHUNK];          // original face id of each staged record
+    const int* fo = face_order ? face_order + (size_t)blockIdx.y * F : nullptr;
     __shared__ __align__(16) float s_rec[PF_CHUNK * PF_REC];
     const int b = blockIdx.y;
     const int slot = blockIdx.x * PF_THREADS + threadIdx.x;
@@ -208,9 +279,45 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
     for (int f0 = 0; f0 < F; f0 += PF_CHUNK) {
         const int nf = min(PF_CHUNK, F - f0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nf; i += PF_THREADS) build_face_record(vb, faces, f0 + i, s_rec + i * PF_REC);
+        for (int i = threadIdx.x; i < nf; i += PF_THREADS) {
+            const int fid = fo ? fo[f0 + i] : f0 + i;
+            s_fid[i] = (unsigned short)fid;
+            build_face_record(vb, faces, fid, s_rec + i * PF_REC);
+        }
         __syncthreads();
-        for (int f = 0; f < nf; ++f) {
+        const int ng = (nf + PF_GROUP - 1) / PF_GROUP;
+        if (fo) {
+            // group spheres: centre = mean of the members' sphere centres, radius = farthest member sphere surface
+            // (a member that is never culled - radius 1e18 - makes its group unculled as well)
+            for (int g = threadIdx.x; g < ng; g += PF_THREADS) {
+                const int a0 = g * PF_GROUP, a1 = min(nf, a0 + PF_GROUP);
+                V3 cm = v3(0.f, 0.f, 0.f);
+                for (int i = a0; i < a1; ++i) {
+                    const float* r = s_rec + i * PF_REC;
+                    cm = cm + v3(r[0] + r[20], r[1] + r[21], r[2] + r[22]);
+                }
+                cm = cm * (1.f / (float)(a1 - a0));
+                float rg = 0.f;
+                for (int i = a0; i < a1; ++i) {
+                    const float* r = s_rec + i * PF_REC;
+                    const V3 d = v3(r[0] + r[20], r[1] + r[21], r[2] + r[22]) - cm;
+                    rg = fmaxf(rg, sqrtf(dot(d, d)) + r[23]);
+                }
+                s_grp[g] = make_float4(cm.x, cm.y, cm.z, rg * 1.0001f + 1e-12f);
+            }
+            __syncthreads();
+        }
+        for (int g = 0; g < ng; ++g) {
+          if (fo) {
+              // one test for the whole group: |p - c_g| > sqrt(best) + r_g implies the same for every member sphere
+              const float4 gs = s_grp[g];
+              const V3 ag = p - v3(gs.x, gs.y, gs.z);
+              const float reach_g = sb + gs.w;
+              if (STATS && live) ++n_grp;
+              if (dot(ag, ag) > reach_g * reach_g * 1.0002f + 1e-30f) continue;
+          }
+          const int fa = g * PF_GROUP, fb = min(nf, fa + PF_GROUP);
+          for (int f = fa; f < fb; ++f) {
             const float4* r4 = reinterpret_cast<const float4*>(s_rec + f * PF_REC);
             const float4 q0 = r4[0], q5 = r4[5];
             const V3 v0 = v3(q0.x, q0.y, q0.z);
@@ -241,7 +348,10 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
                 const float e12 = seg_d2(a - e1, e2 - e1, q4.z);
                 d = fminf(fminf(e01, e02), e12);
             }
-            if (d < best) { best = d; bi = f0 + f; sb = sqrtf(d); }      // strict: lowest face index wins ties
+            // lowest face index wins ties (the staged order is a permutation when face_order is given)
+            const int fid = s_fid[f];
+            if (d < best || (d == best && fid < bi)) { best = d; bi = fid; sb = sqrtf(d); }
+          }
         }
     }
     if (live) {
@@ -249,9 +359,9 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
         idxs[(size_t)b * P + pi] = bi;
     }
     if (STATS) {
-        unsigned int c[3] = {n_cull, n_in, n_edge};
+        unsigned int c[4] = {n_cull, n_in, n_edge, n_grp};
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 4; ++k) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
             if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(stats + k, (unsigned long long)c[k]);
@@ -338,19 +448,25 @@ extern "C" int dsf_point_face_forward(int batch, int P, int V, int F, const floa
     dsf_reset_launch_count();
     DSF_REQUIRE(points && verts && faces && dists && idxs, "null argument");
     DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0 && F > 0, "sizes");
+    DSF_REQUIRE(F <= 65535, "at most 65535 faces");
+    int* face_order = nullptr;
     if (order_ws) {
         point_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(P, points, order_ws);
+        DSF_CHECK_LAUNCH();
+        face_order = order_ws + (size_t)batch * P;
+        face_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(V, F, verts, faces, face_order);
         DSF_CHECK_LAUNCH();
     }
     dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
     point_face_fwd_kernel<false><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
-                                                                              dists, idxs, nullptr);
+                                                                              face_order, dists, idxs, nullptr);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }
 
-// Work counters of the forward scan for the same inputs: stats[0] = pairs rejected by the bounding-sphere test,
-// [1] = pairs evaluated on the interior branch, [2] = on the edge branch (device, 3 x uint64, overwritten).
+// Work counters of the forward scan for the same inputs: stats[0] = pairs rejected by their own bounding-sphere
+// test, [1] = pairs evaluated on the interior branch, [2] = on the edge branch, [3] = group-sphere tests (every
+// remaining pair was rejected with its group); device, 4 x uint64, overwritten.
 // Per pair the scan spends 16 flops on the sphere test (p - v0, offset to the sphere centre, squared norm, reach),
 // 40 more for the plane projection + barycentrics + range checks of an interior hit (56), and 64 more when the
 // three clamped edge distances are needed instead of t^2 (120); multiply, add and compare each count one.
@@ -360,14 +476,19 @@ extern "C" int dsf_point_face_stats(int batch, int P, int V, int F, const float*
     dsf_reset_launch_count();
     DSF_REQUIRE(points && verts && faces && dists && idxs && stats, "null argument");
     DSF_REQUIRE(batch > 0 && batch <= 65535 && P > 0 && V > 0 && F > 0, "sizes");
-    DSF_CHECK_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream));
+    DSF_REQUIRE(F <= 65535, "at most 65535 faces");
+    DSF_CHECK_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream));
+    int* face_order = nullptr;
     if (order_ws) {
         point_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(P, points, order_ws);
+        DSF_CHECK_LAUNCH();
+        face_order = order_ws + (size_t)batch * P;
+        face_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(V, F, verts, faces, face_order);
         DSF_CHECK_LAUNCH();
     }
     dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
     point_face_fwd_kernel<true><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
-                                                                             dists, idxs, stats);
+                                                                             face_order, dists, idxs, stats);
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

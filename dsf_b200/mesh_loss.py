@@ -25,7 +25,7 @@ class _PointFaceDistance(torch.autograd.Function):
         dev = points.device
         dists = torch.empty(B, P, device=dev)
         idxs = torch.empty(B, P, dtype=torch.int32, device=dev)
-        order = torch.empty(B, P, dtype=torch.int32, device=dev)        # scratch: spatial order of the points
+        order = torch.empty(B * (P + F), dtype=torch.int32, device=dev)  # scratch: spatial order of points and faces
         L.check(lib.dsf_point_face_forward(B, P, V, F, points.data_ptr(), verts.data_ptr(), faces_i32.data_ptr(),
                                            dists.data_ptr(), idxs.data_ptr(), order.data_ptr(), L.stream_ptr()))
         ctx.save_for_backward(points, verts, faces_i32, idxs)

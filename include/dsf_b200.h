@@ -191,14 +191,16 @@ int dsf_coll_forward_backward(const DsfMano* h, int batch, const float* joints, 
  * metric/meshLoss.py:21-70 and used by ICPLoss (:347-353) / JointICPLoss (:377-394), with the
  * batch-shared face list DSF always passes.  points (B,P,3), verts (B,V,3),
  * faces (F,3) int32 device pointer -> dists (B,P) squared, idxs (B,P) face index in its mesh. */
-/* order_ws: (B,P) int32 scratch or NULL.  With it the points of each hand are first ordered by a 16^3 grid
- * cell (one extra kernel) so that a warp's points are neighbours and the per-face bounding-sphere test
- * culls whole warps; results are identical either way (the brute-force minimum and arg-min). */
+/* order_ws: (B, P + F) int32 scratch or NULL.  With it the points of each hand, and its faces, are first ordered by
+ * the Morton cell of a 16^3 grid (two small extra kernels) so that a warp's points are neighbours, consecutive
+ * faces share a small bounding sphere, and the scan rejects whole groups of 8 faces with one test before the
+ * per-face bounding-sphere test; results are identical either way (the brute-force minimum and arg-min, lowest
+ * face index on ties). */
 int dsf_point_face_forward(int batch, int P, int V, int F, const float* points, const float* verts,
                            const int* faces, float* dists, int* idxs, int* order_ws, dsfStream_t stream);
 /* dsf_point_face_forward plus work counters for the FP32 roofline of this (compute-bound) row: stats (device,
- * 3 x uint64, overwritten) = pairs rejected by the bounding-sphere test | evaluated, interior branch | evaluated,
- * edge branch. */
+ * 4 x uint64, overwritten) = pairs rejected by their own bounding-sphere test | evaluated, interior branch |
+ * evaluated, edge branch | group-sphere tests (all other pairs fell with their group of 8 faces). */
 int dsf_point_face_stats(int batch, int P, int V, int F, const float* points, const float* verts,
                          const int* faces, float* dists, int* idxs, int* order_ws, unsigned long long* stats,
                          dsfStream_t stream);

@@ -22,7 +22,7 @@ pcl = (torch.gather(v, 1, idx[..., None].expand(-1, -1, 3)) + 0.05 * torch.randn
 faces = layer.faces_int
 d = torch.empty(B, P, device="cuda")
 i = torch.empty(B, P, dtype=torch.int32, device="cuda")
-order = torch.empty(B, P, dtype=torch.int32, device="cuda")
+order = torch.empty(B * (P + faces.shape[0]), dtype=torch.int32, device="cuda")
 g = torch.ones(B, P, device="cuda")
 gp, gv = torch.empty_like(pcl), torch.empty_like(v)
 
