@@ -277,6 +277,13 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     __shared__ float s_theta[POSE_HPB][48];
     __shared__ float s_beta[POSE_HPB][12];
     __shared__ float s_G[POSE_HPB][NJ][15];   // Gr[9] Gt[3] J[3]
+    // the PCA basis and the rest-joint regressors are read 135 + 30 times per lane: stage them once per block
+    // with coalesced loads instead of walking an 8 KB table through L1 one 180-byte row per iteration
+    __shared__ float s_comp[45 * 45];
+    __shared__ float s_JS[10 * NJ * 3];
+    for (int i = threadIdx.x; i < 45 * 45; i += POSE_HPB * NJ) s_comp[i] = __ldg(comp + i);
+    for (int i = threadIdx.x; i < 10 * NJ * 3; i += POSE_HPB * NJ) s_JS[i] = __ldg(JS + i);
+    __syncthreads();
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
     const int hand = blockIdx.x * POSE_HPB + hl;
@@ -305,9 +312,9 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
         ang[0] = mean[a0]; ang[1] = mean[a0 + 1]; ang[2] = mean[a0 + 2];
         for (int k = 0; k < p.ncomp; ++k) {
             float t = s_theta[hl][k];
-            ang[0] = fmaf(t, __ldg(comp + k * 45 + a0), ang[0]);
-            ang[1] = fmaf(t, __ldg(comp + k * 45 + a0 + 1), ang[1]);
-            ang[2] = fmaf(t, __ldg(comp + k * 45 + a0 + 2), ang[2]);
+            ang[0] = fmaf(t, s_comp[k * 45 + a0], ang[0]);
+            ang[1] = fmaf(t, s_comp[k * 45 + a0 + 1], ang[1]);
+            ang[2] = fmaf(t, s_comp[k * 45 + a0 + 2], ang[2]);
         }
         rodrigues(ang, R);
     }
@@ -315,9 +322,9 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
 #pragma unroll
     for (int b = 0; b < 10; ++b) {
         float be = s_beta[hl][b];
-        J[0] = fmaf(be, __ldg(JS + (b * NJ + j) * 3), J[0]);
-        J[1] = fmaf(be, __ldg(JS + (b * NJ + j) * 3 + 1), J[1]);
-        J[2] = fmaf(be, __ldg(JS + (b * NJ + j) * 3 + 2), J[2]);
+        J[0] = fmaf(be, s_JS[(b * NJ + j) * 3], J[0]);
+        J[1] = fmaf(be, s_JS[(b * NJ + j) * 3 + 1], J[1]);
+        J[2] = fmaf(be, s_JS[(b * NJ + j) * 3 + 2], J[2]);
     }
     float* wsh = ws + (size_t)hh * WS_PER_HAND;
     if (live) {
@@ -668,6 +675,11 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
                      LossFold lf) {
     __shared__ float s_acc[POSE_HPB][NJ][15];   // gGr[9] gGt[3] gJ[3]
     __shared__ float s_gang[POSE_HPB][48];
+    __shared__ float s_comp[45 * 45];           // staged once per block, see mano_pose_kernel
+    __shared__ float s_JS[10 * NJ * 3];
+    for (int i = threadIdx.x; i < 45 * 45; i += POSE_HPB * NJ) s_comp[i] = __ldg(comp + i);
+    for (int i = threadIdx.x; i < 10 * NJ * 3; i += POSE_HPB * NJ) s_JS[i] = __ldg(JS + i);
+    __syncthreads();
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
     const int hand = blockIdx.x * POSE_HPB + hl;
@@ -765,7 +777,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     if (live) {
         for (int k = j; k < p.ncomp; k += NJ) {       // angles = theta . comp[:ncomp] + mean
             float a = 0.f;
-            for (int c = 0; c < 45; ++c) a = fmaf(__ldg(comp + k * 45 + c), s_gang[hl][c], a);
+            for (int c = 0; c < 45; ++c) a = fmaf(s_comp[k * 45 + c], s_gang[hl][c], a);
             g.theta[(size_t)hh * g.ld_theta + k] = a;
         }
         if (j < 10) {                                  // direct blend-shape term + rest-joint term
@@ -773,8 +785,8 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
             for (int z = 0; z < n_split; ++z) a += wsh[WS_GX + z * KP + j];
             for (int i = 0; i < NJ; ++i) {
                 const float* gj = &s_acc[hl][i][12];
-                const float* js = JS + (j * NJ + i) * 3;
-                a += __ldg(js) * gj[0] + __ldg(js + 1) * gj[1] + __ldg(js + 2) * gj[2];
+                const float* js = s_JS + (j * NJ + i) * 3;
+                a += js[0] * gj[0] + js[1] * gj[1] + js[2] * gj[2];
             }
             g.beta[(size_t)hh * g.ld_beta + j] = a;
         }

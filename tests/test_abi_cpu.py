@@ -26,7 +26,9 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/dsf_b200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
     assert lib.dsf_version() == 100
-    assert lib.dsf_mano_workspace_floats(3) == 3 * lib.dsf_mano_workspace_floats(1) > 0
+    # the workspace is laid out in groups of 8 hands (the TMA row-group view of the blend GEMM operand)
+    assert lib.dsf_mano_workspace_floats(24) == 3 * lib.dsf_mano_workspace_floats(8) > 0
+    assert lib.dsf_mano_workspace_floats(3) == lib.dsf_mano_workspace_floats(8)
 
 
 def test_sass_is_sm100a():
