@@ -362,10 +362,16 @@ def run_ours(args):
     # every step: H2D of that step's inputs (params, centre, cube, target depth) from pinned memory,
     # the fused step, D2H of loss + parameter gradients.  Two FitStep instances ping-pong so the copy
     # of step i+1 (copy stream) overlaps the compute of step i; all copies stay inside the timed region.
-    steps2 = [step, mk(B)]
+    steps_plain = [step, mk(B)]
+    # row-run transport: the rasteriser's epilogue decodes the packed crop itself (dsf_fit_step_rows)
+    mk_rows = lambda b: FitStep(layer, b, CROP, use_graph=not args.no_graph, chunks=n_chunks(b), keep_pix_to_face=False,
+                                fuse_target_rows=True)
+    steps_rows = [mk_rows(B), mk_rows(B)]
     h_g = [torch.empty(B, 62).pin_memory() for _ in range(2)]
     h_tot = [torch.empty(4).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
+    d2h_stream = torch.cuda.Stream()
+    computed = [torch.cuda.Event() for _ in range(2)]
     main_stream = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
@@ -374,7 +380,8 @@ def run_ours(args):
     d2h = B * 62 * 4 + 16
 
     def measure_e2e(fmt):
-        host_target = host_targets[fmt]
+        host_target = host_targets["u16rows" if fmt == "u16rows_unpack" else fmt]
+        steps2 = steps_rows if fmt == "u16rows" else steps_plain
 
         def upload(i):
             with torch.cuda.stream(copy_stream):
@@ -397,9 +404,13 @@ def run_ours(args):
                     upload(1 - i)
                 main_stream.wait_event(ready[i])
                 steps2[i].step()
-                h_g[i].copy_(steps2[i].g_params, non_blocking=True)
-                h_tot[i].copy_(steps2[i].totals, non_blocking=True)
-                done[i].record(main_stream)
+                computed[i].record(main_stream)
+                with torch.cuda.stream(d2h_stream):          # results leave on their own stream, under step i+1
+                    d2h_stream.wait_event(computed[i])
+                    h_g[i].copy_(steps2[i].g_params, non_blocking=True)
+                    h_tot[i].copy_(steps2[i].totals, non_blocking=True)
+                    done[i].record(d2h_stream)
+            d2h_stream.synchronize()
             main_stream.synchronize()
 
         e2e_run()
@@ -412,26 +423,30 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         t = D.max_over_ranks(e0.elapsed_time(e1) / e2e_iters, dev)
-        h2d = B * (62 + 3 + 3) * 4 + (packed.nbytes if fmt == "u16rows" else B * CROP * CROP * (2 if fmt == "u16" else 4))
+        h2d = B * (62 + 3 + 3) * 4 + (packed.nbytes if fmt.startswith("u16rows") else B * CROP * CROP * (2 if fmt == "u16" else 4))
         return {"value": G / (t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "ms_per_step": t, "target_format": fmt,
-                "note": "double-buffered: H2D of step i+1 overlaps compute of step i; %.1f MB in per step on this rank; "
+                "note": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap compute of step i; %.1f MB in per step on this rank; "
                         "target crop travels as %s" % (h2d / 1e6, {
                             "u16": "the sensor's uint16 mm, normalised on the device (dsf_target_from_u16)",
                             "f32": "loader-normalised fp32 (the reference's own hand-off)",
                             "u16rows": "row-run packed uint16 mm (per row only the span between the first and the last "
-                                       "non-background pixel; packed by the loader with dsf_pack_u16_rows, unpacked + "
-                                       "normalised on the device by dsf_target_from_u16_rows)"}[fmt])}
+                                       "non-background pixel; packed by the loader with dsf_pack_u16_rows, decoded + "
+                                       "normalised inside the rasteriser's epilogue: dsf_fit_step_rows, no unpack launch, "
+                                       "no fp32 target plane)",
+                            "u16rows_unpack": "row-run packed uint16 mm, unpacked to an fp32 plane by a separate kernel "
+                                              "(dsf_target_from_u16_rows) before the step"}[fmt])}
 
     e2e = measure_e2e(args.target_format)
-    e2e_others = {f: measure_e2e(f) for f in ("u16rows", "u16", "f32") if f != args.target_format}
+    e2e_others = {f: measure_e2e(f) for f in ("u16rows", "u16rows_unpack", "u16", "f32") if f != args.target_format}
     allv = dict(e2e_others)
     allv[args.target_format] = e2e
     # all hand-offs belong next to each other: the reference uploads the loader-normalised fp32 crop
     e2e["note"] += ("; the three hand-offs side by side: reference-style fp32 crop %.3g fits/s, sensor uint16 crop "
-                    "%.3g fits/s, row-run packed uint16 crop %.3g fits/s (packing is loader work, once per sample: "
-                    "%.2f us per hand on one host core here)"
-                    % (allv["f32"]["value"], allv["u16"]["value"], allv["u16rows"]["value"], 1e6 * t_pack / B))
+                    "%.3g fits/s, row-run packed uint16 crop %.3g fits/s decoded in the rasteriser (%.3g with a separate unpack "
+                    "kernel) (packing is loader work, once per sample: %.2f us per hand on one host core here)"
+                    % (allv["f32"]["value"], allv["u16"]["value"], allv["u16rows"]["value"],
+                       allv["u16rows_unpack"]["value"], 1e6 * t_pack / B))
 
     if rank != 0:
         return

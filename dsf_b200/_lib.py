@@ -77,6 +77,8 @@ SIGNATURES = {
     "dsf_fit_workspace_floats": (_L, [_I, _I]),
     "dsf_fit_step": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I, _VP, _I, _VP, c_float_p,
                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dsf_fit_step_rows": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _F, _I, _VP, _I, _VP, c_float_p,
+                               _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dsf_raster_loss_workspace_floats": (_L, [_I, _I]),
     "dsf_raster_loss_grad": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _F, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dsf_sum_totals": (_I, [_I, _VP, _I, _VP, _VP]),

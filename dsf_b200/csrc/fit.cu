@@ -16,21 +16,23 @@ extern "C" long dsf_fit_workspace_floats(int batch, int R) {
     return WS_HANDS(batch) * WS_PER_HAND + (long)batch * (2L * nt + nt + nt * NVW * 3) + 4;
 }
 
-extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
-                            const float* cube, const float* view, const float* xs, const float* ys,
-                            const float* target, float loss_weight, int norm_batch, const float* crop_joints,
-                            int n_crop_joints,
-                            const float* crop_M, const float* intr4, float* img, int* pix_to_face,
-                            float* verts, float* joints, float* g_params, float* parts, float* totals,
-                            float* workspace, int flags, dsfStream_t stream) {
+static int fit_step_impl(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
+                         const float* cube, const float* view, const float* xs, const float* ys,
+                         const float* target, const TargetRows* trows, float loss_weight, int norm_batch,
+                         const float* crop_joints, int n_crop_joints,
+                         const float* crop_M, const float* intr4, float* img, int* pix_to_face,
+                         float* verts, float* joints, float* g_params, float* parts, float* totals,
+                         float* workspace, int flags, dsfStream_t stream) {
     dsf_reset_launch_count();
-    DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && target, "null input");
+    DSF_REQUIRE(h && params && center3d && cube && view && xs && ys && (target || trows), "null input");
     DSF_REQUIRE(img && verts && joints && g_params && parts && totals && workspace, "null output");
     DSF_REQUIRE(batch > 0 && batch <= 65535, "batch must be in [1,65535] per call");
     DSF_REQUIRE(R >= 8 && R <= 512, "crop size R must be in [8,512]");
     const bool fused = dsf_raster_fused_grad_ok(h, flags);
     DSF_REQUIRE(fused || pix_to_face, "pix_to_face may only be NULL when the rasteriser produces the gradient itself "
                                       "(no perspective correction)");
+    DSF_REQUIRE(fused || target, "the row-run target needs the step whose rasteriser produces the gradient itself "
+                                 "(flags without PERSPECTIVE_CORRECT / SEPARATE_BACKWARD)");
     cudaStream_t st = (cudaStream_t)stream;
     float* ws_mano = workspace;
     const int n_tiles = dsf_raster_tiles(R);
@@ -66,7 +68,7 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     // (parts by the skinning backward, totals by block 0 of the pose backward): no fold / totals launches.
     RasterFused rf = {fused ? gv_tile : nullptr, gv_flag};
     rc = dsf_raster_forward_impl(h, batch, verts, cube, center3d, view, xs, ys, R, img, pix_to_face, nullptr,
-                                 nullptr, nullptr, target, thr, parts_tile, cropp, flags, &rf, st);
+                                 nullptr, nullptr, target, thr, parts_tile, cropp, flags, &rf, st, target ? nullptr : trows);
     if (rc) return rc;
     LossFold lf = {parts_tile, n_tiles, batch, parts, totals, loss_weight};
     if (fused) {
@@ -81,6 +83,39 @@ extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* par
     if (rc) return rc;
     return dsf_mano_backward_impl(h, batch, &p, unit_scale, verts, joints, g_verts, nullptr, &g, ws_mano, nullptr,
                                   nullptr, &lf, st);
+}
+
+extern "C" int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
+                            const float* cube, const float* view, const float* xs, const float* ys,
+                            const float* target, float loss_weight, int norm_batch, const float* crop_joints,
+                            int n_crop_joints,
+                            const float* crop_M, const float* intr4, float* img, int* pix_to_face,
+                            float* verts, float* joints, float* g_params, float* parts, float* totals,
+                            float* workspace, int flags, dsfStream_t stream) {
+    DSF_REQUIRE(target, "null input");
+    return fit_step_impl(h, batch, R, params, center3d, cube, view, xs, ys, target, nullptr, loss_weight, norm_batch,
+                         crop_joints, n_crop_joints, crop_M, intr4, img, pix_to_face, verts, joints, g_params, parts,
+                         totals, workspace, flags, stream);
+}
+
+// The same step with the target still in the loader's row-run transport format (dsf_pack_u16_rows): the rasteriser's
+// epilogue decodes + normalises the sensor pixels where it compares them, so neither the unpack launch nor the fp32
+// target plane (64 KB per hand written and read back) exists.  rows / hand_offset point at the first hand of this
+// call (hand_offset holds absolute pixel offsets into payload, so slices of a batch share one payload).
+extern "C" int dsf_fit_step_rows(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
+                                 const float* cube, const float* view, const float* xs, const float* ys,
+                                 const unsigned short* rows, const unsigned int* hand_offset,
+                                 const unsigned short* payload, int invalid_value, float loss_weight, int norm_batch,
+                                 const float* crop_joints, int n_crop_joints, const float* crop_M, const float* intr4,
+                                 float* img, int* pix_to_face, float* verts, float* joints, float* g_params,
+                                 float* parts, float* totals, float* workspace, int flags, dsfStream_t stream) {
+    DSF_REQUIRE(rows && hand_offset && payload, "null row-run target");
+    DSF_REQUIRE((((size_t)rows) & 3) == 0, "rows must be 4-byte aligned");
+    DSF_REQUIRE(invalid_value >= 0 && invalid_value <= 65535, "invalid_value must fit uint16 (0 = none)");
+    TargetRows tr = {rows, hand_offset, payload, (unsigned)invalid_value};
+    return fit_step_impl(h, batch, R, params, center3d, cube, view, xs, ys, nullptr, &tr, loss_weight, norm_batch,
+                         crop_joints, n_crop_joints, crop_M, intr4, img, pix_to_face, verts, joints, g_params, parts,
+                         totals, workspace, flags, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@
 // consumers - ICP losses and seg_pcl - are permutation invariant).
 #include <math.h>
 
-#include "common.cuh"
+#include "raster.cuh"
 
 #define PCL_THREADS 512
 #define PCL_WARPS (PCL_THREADS / 32)
@@ -326,14 +326,6 @@ extern "C" int dsf_uvd_img_to_xyz(int batch, int R, const float* img, const floa
 // (normalize_img :738-745) and ships 4 bytes per pixel to the GPU; here the crop travels as the
 // sensor's own uint16 (half the PCIe bytes) and :738-745 runs in this kernel, same operation order.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float target_norm(unsigned u, unsigned invalid, float cz, float hz, float far_, float near_) {
-    float v = (float)u;
-    if (u == 0u || (invalid && u == invalid)) v = far_;
-    if (v >= far_) v = far_;
-    if (v <= near_) v = near_;
-    return __fdiv_rn(__fsub_rn(v, cz), hz);
-}
-
 __global__ void __launch_bounds__(256)
 target_from_u16_kernel(int npix, const unsigned short* __restrict__ depth, const float* __restrict__ center,
                        const float* __restrict__ cube, unsigned invalid, float* __restrict__ out) {

@@ -500,7 +500,7 @@ struct FusedTail {
     int* gv_flag;                    // (n_mesh, tiles) 1 = gv_tile row written, 0 = tile carries no gradient
 };
 
-template <bool PERSP>
+template <bool PERSP, bool ROWS>
 __global__ void __launch_bounds__(RT_THREADS, 2)
 raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const float* __restrict__ place_scale,
                   const float* __restrict__ place_off, const unsigned int* __restrict__ faces_packed,
@@ -508,9 +508,12 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   const float* __restrict__ view, const float* __restrict__ xs_g, const float* __restrict__ ys_g,
                   float* __restrict__ img, int* __restrict__ p2f, float* __restrict__ zbuf,
                   float* __restrict__ bary, float* __restrict__ dists, const float* __restrict__ target,
-                  float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop, FusedTail tail) {
+                  float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop, FusedTail tail,
+                  TargetRows trows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RasterSmem s = carve_smem(smem_raw, R, F);
+    // the loss target either as an fp32 plane or in the loader's row-run transport format (decoded in the epilogue)
+    const bool has_target = target != nullptr || (ROWS && trows.rows != nullptr);
     const int mesh = blockIdx.y;
     const int tile = blockIdx.x;
     const int tx0 = (tile % tiles_x) * RT_TW, ty0 = (tile / tiles_x) * RT_TH;
@@ -527,6 +530,17 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         for (int i = tid; i < rows * lines_per_row; i += RT_THREADS) {
             const float* pa = target + ((size_t)mesh * R + ty0 + i / lines_per_row) * R + tx0 + (i % lines_per_row) * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
+    } else if (ROWS && trows.rows && tid < 64) {
+        // row-run target: this hand's row records and packed pixels (a few KB) go to L2 now, behind the raster work
+        if (tid < 32) {
+            const char* rr = reinterpret_cast<const char*>(trows.rows + (size_t)mesh * R * 2);
+            for (int i = tid * 128; i < R * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rr + i));
+        } else {
+            const unsigned int p0 = __ldg(trows.hand_offset + mesh), p1 = __ldg(trows.hand_offset + mesh + 1);
+            const char* pp = reinterpret_cast<const char*>(trows.payload);
+            for (size_t i = ((size_t)p0 * 2 & ~(size_t)127) + (size_t)(tid - 32) * 128; i < (size_t)p1 * 2; i += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + i));
         }
     }
     if (use_tma) {
@@ -757,7 +771,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     unsigned short* flist = reinterpret_cast<unsigned short*>(mom + 3 * Fp);        // per-warp lists of touched faces (after the
                                                                                     // pixel loop; before, its group lists)
     int* sgn = reinterpret_cast<int*>(flist + Fp);                                  // (NVW,3) NDC vertex gradients, fixed point
-    const bool do_crop = target && crop.joints;
+    const bool do_crop = has_target && crop.joints;
     // Fused backward (no perspective correction): the depth of a face is affine in the sample position,
     // pz(p) = [z0 e0(p) + z1 e1(p) + z2 e2(p)] / area, so the whole zbuf cotangent of a face collapses to the
     // three moments (sum g, sum g px, sum g py) over its pixels, and d loss / d img of the m2d loss is
@@ -770,7 +784,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     // the vertices are chained through the projection.  The per-hand factor gk / zhalf is applied by the consumer
     // (it needs the mask count of all tiles).  No pix_to_face plane, no second pass over target / img, no backward
     // kernel, bit-reproducible.
-    const bool do_grad = !PERSP && tail.gv_tile != nullptr && target != nullptr;
+    const bool do_grad = !PERSP && tail.gv_tile != nullptr && has_target;
     if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
     const float cx0s = s.xs[tx0], cy0s = s.ys[ty0];
     const int q0x = (cx0s == cx0s) ? __float2int_rn(((1.f - cx0s) * vw.S - 1.f) * 0.5f) : 0;
@@ -801,6 +815,56 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         // (2) the list is processed with all lanes busy (a row through the hand has ~1/3 of its groups on the hand).
         const float bgval = __fdiv_rn(__fsub_rn(zmax, vw.zc), vw.zh);
         const int qw = tw >> 2;
+        // row-run target: lane r of the warp keeps the span record and the payload offset of the warp's r-th row
+        // (rows warp, warp + 16, ...: at most four of the 64-row tile); the offsets are prefix sums of the row lengths
+        unsigned int my_rec = 0u, my_off = 0u;
+        if (ROWS && trows.rows) {
+            // one warp scan per 128 rows: lane l owns rows 4 l .. 4 l + 3 (one 128-bit load of their records), the
+            // exclusive prefix of the lengths is each row's payload offset; the warp's rows fetch theirs by shuffle
+            const unsigned int* r32 = reinterpret_cast<const unsigned int*>(trows.rows) + (size_t)mesh * R;
+            unsigned int carry = __ldg(trows.hand_offset + mesh);
+            for (int c0 = 0; c0 < ty0 + th; c0 += 128) {
+                const int q = c0 + 4 * lane;
+                uint4 rc = make_uint4(0u, 0u, 0u, 0u);
+                if (q + 3 < R) rc = __ldg(reinterpret_cast<const uint4*>(r32 + q));       // R % 4 == 0 on this path
+                const unsigned int e1 = rc.x >> 16, e2 = e1 + (rc.y >> 16), e3 = e2 + (rc.z >> 16), tot = e3 + (rc.w >> 16);
+                unsigned int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const unsigned int excl = carry + incl - tot;
+#pragma unroll
+                for (int r = 0; r < RT_TH / (RT_THREADS / 32); ++r) {
+                    const int ly = warp + r * (RT_THREADS / 32), g = ty0 + ly - c0;      // warp-uniform
+                    if (ly < th && g >= 0 && g < 128) {
+                        const int sub = g & 3;
+                        const unsigned int o_v = excl + (sub == 0 ? 0u : sub == 1 ? e1 : sub == 2 ? e2 : e3);
+                        const unsigned int r_v = sub == 0 ? rc.x : sub == 1 ? rc.y : sub == 2 ? rc.z : rc.w;
+                        const unsigned int o_g = __shfl_sync(0xffffffffu, o_v, g >> 2), r_g = __shfl_sync(0xffffffffu, r_v, g >> 2);
+                        if (lane == r) { my_off = o_g; my_rec = r_g; }
+                    }
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        // the four target values of a pixel group: fp32 plane, or decoded from the row's span (outside it the value
+        // target_norm gives depth 0, which is bgval)
+        auto target4 = [&](size_t o, unsigned int rec, unsigned int off, int x) -> float4 {
+            if (!ROWS || target) return __ldg(reinterpret_cast<const float4*>(target + o));
+            float t[4] = {bgval, bgval, bgval, bgval};
+            const int s0 = (int)(rec & 0xffffu), n = (int)(rec >> 16);
+            if (x + 3 >= s0 && x < s0 + n) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k = x + c - s0;
+                    if ((unsigned int)k < (unsigned int)n)
+                        t[c] = target_norm(__ldg(trows.payload + off + k), trows.invalid, vw.zc, vw.zh, zmax, zmin_c);
+                }
+            }
+            return make_float4(t[0], t[1], t[2], t[3]);
+        };
         // general group: depth normalisation, loss terms, moments of the loss gradient
         auto process_group = [&](int ly, int lx, const float4& tg, const ulonglong2& k01, const ulonglong2& k23) {
             const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
@@ -825,7 +889,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                     ff[c] = (int)(unsigned int)(kk[c] & 0xffffffffu);
                     grad_ok = z > 0.f && !(z > zmax) && !(z < zmin_c);
                 }
-                if (target) {
+                if (has_target) {
                     const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx + c, R, v[c], vw.zc, vw.zh));
                     const float vc = kept ? v[c] : 1.f;
                     const bool m = tt[c] < thr || vc < thr;
@@ -853,21 +917,32 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         const bool use_list = qw <= 32 && th <= 4 * (RT_THREADS / 32) && Fp * 2 >= (RT_THREADS / 32) * 128;
         int n_list = 0;
         for (int ly = warp, r = 0; ly < th; ly += RT_THREADS / 32, ++r) {
+            const unsigned int rec = ROWS ? __shfl_sync(0xffffffffu, my_rec, r & 31) : 0u;
+            const unsigned int off = ROWS ? __shfl_sync(0xffffffffu, my_off, r & 31) : 0u;
             for (int q4 = lane; q4 < ((qw + 31) & ~31); q4 += 32) {
                 const bool in = q4 < qw;
                 const int lx = q4 * 4;
                 const size_t o = ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx);
                 float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
                 ulonglong2 k01 = make_ulonglong2(~0ull, ~0ull), k23 = k01;
+                // row-run target: groups that touch the row's span are decoded in pass 2 (all lanes busy there; in
+                // this row-ordered pass only the lanes over the span would work); everywhere else the target is bgval
+                bool in_span = false;
                 if (in) {
-                    if (target) tg = __ldg(reinterpret_cast<const float4*>(target + o));
+                    if (ROWS && !target) {
+                        const int s0 = (int)(rec & 0xffffu), x = tx0 + lx;
+                        in_span = has_target && x + 3 >= s0 && x < s0 + (int)(rec >> 16);
+                        tg = make_float4(bgval, bgval, bgval, bgval);
+                    } else if (has_target) {
+                        tg = target4(o, rec, off, tx0 + lx);
+                    }
                     k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
                     k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
                 }
-                const bool all_bg = (k01.x & k01.y & k23.x & k23.y) == ~0ull && !do_crop;
+                const bool all_bg = (k01.x & k01.y & k23.x & k23.y) == ~0ull && !do_crop && !in_span;
                 if (in && all_bg) {
                     // four background pixels: far plane out, loss only where the target has depth
-                    if (target) {
+                    if (has_target) {
                         const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
@@ -882,17 +957,22 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                     if (general) glist[n_list + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)((r << 5) | q4);
                     n_list += __popc(mk);
                 } else if (general) {
+                    if (ROWS && !target && has_target) tg = target4(o, rec, off, tx0 + lx);
                     process_group(ly, lx, tg, k01, k23);
                 }
             }
         }
         if (use_list) {
             __syncwarp();
-            for (int k = lane; k < n_list; k += 32) {
-                const int e = glist[k];
+            for (int k0 = 0; k0 < n_list; k0 += 32) {
+                const int k = k0 + lane;
+                const int e = k < n_list ? glist[k] : 0;
+                const unsigned int rec = ROWS ? __shfl_sync(0xffffffffu, my_rec, e >> 5) : 0u;
+                const unsigned int off = ROWS ? __shfl_sync(0xffffffffu, my_off, e >> 5) : 0u;
+                if (k >= n_list) continue;
                 const int ly = warp + (e >> 5) * (RT_THREADS / 32), lx = (e & 31) * 4;
                 float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (target) tg = __ldg(reinterpret_cast<const float4*>(target + ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx)));
+                if (has_target) tg = target4(((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx), rec, off, tx0 + lx);
                 const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
                 const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx + 2]);
                 process_group(ly, lx, tg, k01, k23);
@@ -907,6 +987,23 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             for (int q = 0; q < RT_TW / 32; ++q) {
                 const int lx = lane + 32 * q;
                 tg[q] = lx < tw ? __ldg(target + ((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx)) : 1.f;
+            }
+        } else if (ROWS && trows.rows) {
+            // row-run target, general path: the row's payload offset = prefix sum of the lengths of the rows above
+            const unsigned int* r32 = reinterpret_cast<const unsigned int*>(trows.rows) + (size_t)mesh * R;
+            unsigned int off = 0u;
+            for (int q0 = 0; q0 < ty0 + ly; q0 += 32) off += q0 + lane < ty0 + ly ? __ldg(r32 + q0 + lane) >> 16 : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+            off += __ldg(trows.hand_offset + mesh);
+            const unsigned int rec = __ldg(r32 + ty0 + ly);
+            const int s0 = (int)(rec & 0xffffu), n = (int)(rec >> 16);
+            const float bgt = __fdiv_rn(__fsub_rn(zmax, vw.zc), vw.zh);
+#pragma unroll
+            for (int q = 0; q < RT_TW / 32; ++q) {
+                const int k = tx0 + lane + 32 * q - s0;
+                tg[q] = (unsigned int)k < (unsigned int)n
+                            ? target_norm(__ldg(trows.payload + off + k), trows.invalid, vw.zc, vw.zh, zmax, zmin_c) : bgt;
             }
         }
 #pragma unroll
@@ -924,7 +1021,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const float val = __fdiv_rn(__fsub_rn(d, vw.zc), vw.zh);
             img[o] = val;
             if (p2f) p2f[o] = f;
-            if (target) {
+            if (has_target) {
                 const float t = tg[q];
                 const bool kept = !(do_crop && !crop_keep(*cbox, crop, ty0 + ly, tx0 + lx, R, val, vw.zc, vw.zh));
                 const float vc = kept ? val : 1.f;
@@ -1069,7 +1166,7 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
                             const float* target, float thr, float* parts_tile, const CropParams* crop,
-                            int flags, const RasterFused* fused, cudaStream_t st) {
+                            int flags, const RasterFused* fused, cudaStream_t st, const TargetRows* trows) {
     if (h->n_faces > RT_MAXF) {
         dsf_set_error("rasteriser supports at most %d faces (got %d)", RT_MAXF, h->n_faces);
         return DSF_ERR_UNSUPPORTED;
@@ -1081,9 +1178,11 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 16 || !attr_set[dev]) {
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
-        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
+        DSF_CHECK_CUDA(cudaFuncSetAttribute(raster_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)raster_fwd_smem(RT_MAXR, RT_MAXF)));
         if (dev < 16) attr_set[dev] = true;
     }
@@ -1096,10 +1195,15 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
     const int use_tma = (R % 4 == 0) && ((uintptr_t)verts % 16 == 0) && ((uintptr_t)xs % 16 == 0) &&
                         ((uintptr_t)ys % 16 == 0);
     dim3 grid(tiles_x * tiles_y, n_mesh);
-    auto kern = persp ? raster_fwd_kernel<true> : raster_fwd_kernel<false>;
+    if (trows && (persp || target)) {
+        dsf_set_error("the row-run target replaces the fp32 target and needs the non-perspective-correct rasteriser");
+        return DSF_ERR_UNSUPPORTED;
+    }
+    auto kern = persp ? raster_fwd_kernel<true, false> : (trows ? raster_fwd_kernel<false, true> : raster_fwd_kernel<false, false>);
     kern<<<grid, RT_THREADS, smem, st>>>(R, tiles_x, verts, place_scale, place_off, h->faces_packed, h->face_order,
                                          h->n_faces, view, xs, ys, img, p2f, zbuf, bary, dists, target, thr,
-                                         parts_tile, use_tma, crop ? *crop : CropParams{}, tail);
+                                         parts_tile, use_tma, crop ? *crop : CropParams{}, tail,
+                                         trows ? *trows : TargetRows{});
     DSF_CHECK_LAUNCH();
     return DSF_OK;
 }

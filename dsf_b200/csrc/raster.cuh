@@ -12,6 +12,25 @@ struct CropParams {
     float off_xy, off_z, thick;
 };
 
+// The target of the m2d loss in the loader's row-run transport format (dsf_pack_u16_rows): the rasteriser's
+// epilogue decodes and normalises it on the fly, so the sensor crop never exists as an fp32 plane in HBM.
+struct TargetRows {
+    const unsigned short* rows;        // (n_mesh, R, 2) uint16 (first column, length) of every row's span, or null
+    const unsigned int* hand_offset;   // (n_mesh + 1) start of each hand's pixels in the payload
+    const unsigned short* payload;     // packed uint16 millimetres
+    unsigned invalid;                  // sensor's "no measurement" marker besides 0 (0 = none)
+};
+
+// loader.normalize_img of one sensor pixel (data/render_loader.py:738-745), same operation order:
+// background / invalid -> far plane, clamp to the cube, (v - centre_z) / half_depth
+__device__ __forceinline__ float target_norm(unsigned u, unsigned invalid, float cz, float hz, float far_, float near_) {
+    float v = (float)u;
+    if (u == 0u || (invalid && u == invalid)) v = far_;
+    if (v >= far_) v = far_;
+    if (v <= near_) v = near_;
+    return __fdiv_rn(__fsub_rn(v, cz), hz);
+}
+
 // optional fused tail of the raster forward launch (see raster_fwd_kernel)
 struct RasterFused {
     float* gv_tile;               // (n_mesh, tiles, NVW*3) per-tile vertex-gradient shares, or null
@@ -60,7 +79,7 @@ int dsf_raster_forward_impl(const DsfMano* h, int n_mesh, const float* verts, co
                             const float* place_off, const float* view, const float* xs, const float* ys,
                             int R, float* img, int* p2f, float* zbuf, float* bary, float* dists,
                             const float* target, float thr, float* parts_tile, const CropParams* crop,
-                            int flags, const RasterFused* fused, cudaStream_t st);
+                            int flags, const RasterFused* fused, cudaStream_t st, const TargetRows* trows = nullptr);
 int dsf_raster_backward_impl(const DsfMano* h, int n_mesh, const float* verts, const float* place_scale,
                              const float* place_off, const float* view, const float* xs, const float* ys,
                              int R, const int* p2f, const float* g_img, float* g_verts, const float* target,

@@ -25,11 +25,13 @@ class FitStep:
     with (pytorch3d 0.4.0 default, see include/dsf_b200.h).  keep_pix_to_face=False drops the pix_to_face
     plane, which nothing reads once the rasteriser emits the vertex gradient itself (default settings only).
     The per-hand view records depend only on (center3d, cube): they are rebuilt by set_inputs(), not by
-    every step()."""
+    every step().  fuse_target_rows=True: a row-run packed target (pcl.RowRunTarget) handed to set_inputs() is
+    not unpacked into ``self.target``; the rasteriser's epilogue decodes it in place (dsf_fit_step_rows - no unpack
+    launch, no fp32 target plane; ``materialise_target()`` rebuilds ``self.target`` on demand)."""
 
     def __init__(self, mano_layer, batch, crop=128, cam_para=(588.03, 587.07, 320.0, 240.0),
                  image_size=(640, 480), mode="direct", loss_weight=0.1, use_graph=True, device=None, chunks=1,
-                 perspective_correct=False, keep_pix_to_face=True):
+                 perspective_correct=False, keep_pix_to_face=True, fuse_target_rows=False):
         self.lib = L.lib()
         self.flags = L.RASTER_PERSPECTIVE_CORRECT if perspective_correct else 0
         if mode == "literal":
@@ -38,6 +40,10 @@ class FitStep:
             self.flags |= L.RASTER_SEPARATE_BACKWARD
         if self.flags and not keep_pix_to_face:
             raise ValueError("only the direct-mode, non-perspective-correct step can drop the pix_to_face plane")
+        if self.flags and fuse_target_rows:
+            raise ValueError("only the direct-mode, non-perspective-correct step can decode the row-run target in place")
+        self.fuse_target_rows = bool(fuse_target_rows)
+        self._rows_active = False         # the step reads the row-run buffers instead of self.target
         self.layer = mano_layer
         self.B, self.R = int(batch), int(crop)
         self.mode = _MODES[mode]
@@ -103,6 +109,13 @@ class FitStep:
                     self._row_bufs = (torch.empty(self.B, self.R, 2, dtype=torch.uint16, device=dev),
                                       torch.empty(self.B + 1, dtype=torch.int32, device=dev),
                                       torch.empty(self.B * self.R * self.R, dtype=torch.uint16, device=dev))
+                if self.fuse_target_rows:
+                    d_rows, d_off, d_pay = self._row_bufs
+                    d_rows.copy_(target.rows, non_blocking=True)
+                    d_off.copy_(target.hand_offset, non_blocking=True)
+                    d_pay[:target.payload.numel()].copy_(target.payload, non_blocking=True)
+                    self._set_rows_active(True)
+                    return
                 target_from_u16_rows(target, self.center3d, self.cube, 0, out=self.target, buffers=self._row_bufs)
             elif target.dtype == torch.uint16:
                 # sensor format: uint16 millimetres travel over PCIe (half the bytes), normalised here
@@ -114,6 +127,22 @@ class FitStep:
                                                      self.target.data_ptr(), L.stream_ptr()))
             else:
                 self.target.copy_(target.reshape(self.B, self.R, self.R), non_blocking=True)
+            self._set_rows_active(False)
+
+    def _set_rows_active(self, on):
+        if on != self._rows_active:
+            self._rows_active = on
+            self._graph = None               # the captured launch sequence reads the other target buffers
+
+    def materialise_target(self):
+        """Rebuild ``self.target`` (normalised fp32) from the row-run buffers of the last set_inputs()."""
+        if self._row_bufs is None:
+            return self.target
+        d_rows, d_off, d_pay = self._row_bufs
+        L.check(self.lib.dsf_target_from_u16_rows(self.B, self.R, d_rows.data_ptr(), d_off.data_ptr(), d_pay.data_ptr(),
+                                                  self.center3d.data_ptr(), self.cube.data_ptr(), 0,
+                                                  self.target.data_ptr(), L.stream_ptr()))
+        return self.target
 
     def set_crop_joints(self, joints):
         """Teacher joints (B,J,3) in normalised cube units: the rendered image is passed through
@@ -137,6 +166,18 @@ class FitStep:
         def run_chunk(c):
             lo, hi = self._bounds[c]
             off = lambda t, per: t.data_ptr() + lo * per * t.element_size()
+            if self._rows_active:
+                d_rows, d_off, d_pay = self._row_bufs
+                L.check(self.lib.dsf_fit_step_rows(
+                    self.layer._handle, hi - lo, self.R, off(self.params, 62), off(self.center3d, 3),
+                    off(self.cube, 3), off(self.view, L.VIEW_STRIDE), off(self.xs, self.R), off(self.ys, self.R),
+                    off(d_rows, 2 * self.R), off(d_off, 1), d_pay.data_ptr(), 0, self.loss_weight, self.B,
+                    None if self.crop_joints is None else off(self.crop_joints, nj * 3), nj, off(self.M, 9),
+                    self._intr, off(self.img, R2), None if self.p2f is None else off(self.p2f, R2),
+                    off(self.verts, L.NVW * 3), off(self.joints, L.NJOUT * 3), off(self.g_params, 62), off(self.parts, 2),
+                    self.totals.data_ptr() if self.chunks == 1 else self.chunk_totals[c].data_ptr(),
+                    self.ws[c].data_ptr(), self.flags, L.stream_ptr()))
+                return self.lib.dsf_last_launch_count()
             L.check(self.lib.dsf_fit_step(
                 self.layer._handle, hi - lo, self.R, off(self.params, 62), off(self.center3d, 3),
                 off(self.cube, 3), off(self.view, L.VIEW_STRIDE), off(self.xs, self.R), off(self.ys, self.R),
@@ -182,6 +223,7 @@ class FitStep:
         """Fill self.target with the rendering of another parameter set (synthetic 'real' depth)."""
         keep = self.params.clone()
         self.params.copy_(params_target)
+        self._set_rows_active(False)
         self.target.fill_(1.0)
         self._view_setup()
         self._enqueue()

@@ -257,6 +257,21 @@ int dsf_fit_step(const DsfMano* h, int batch, int R, const float* params, const 
                  float* verts, float* joints, float* g_params, float* parts, float* totals,
                  float* workspace, int flags, dsfStream_t stream);
 
+/* The same step fed straight from the loader's row-run transport format (dsf_pack_u16_rows below; replaces
+ * data/render_loader.py:738-745 + the fp32 upload + train_render.py:728-732): the rasteriser's epilogue decodes and
+ * normalises the sensor pixels where it compares them, so there is no unpack launch and no fp32 target plane in
+ * HBM.  rows (batch,R,2) / hand_offset (batch+1) point at the first hand of this call; hand_offset holds absolute
+ * pixel offsets into payload, so the slices of a batch share one payload.  Needs flags without
+ * DSF_RASTER_PERSPECTIVE_CORRECT / DSF_RASTER_SEPARATE_BACKWARD.  Results are bit-identical to dsf_fit_step on the
+ * target dsf_target_from_u16_rows rebuilds. */
+int dsf_fit_step_rows(const DsfMano* h, int batch, int R, const float* params, const float* center3d,
+                      const float* cube, const float* view, const float* xs, const float* ys,
+                      const unsigned short* rows, const unsigned int* hand_offset, const unsigned short* payload,
+                      int invalid_value, float loss_weight, int norm_batch, const float* crop_joints,
+                      int n_crop_joints, const float* crop_M, const float* intr4, float* img, int* pix_to_face,
+                      float* verts, float* joints, float* g_params, float* parts, float* totals,
+                      float* workspace, int flags, dsfStream_t stream);
+
 /* totals (4) of one batch that ran as n_slices dsf_fit_step calls (slice_totals (n_slices,4), each with
  * norm_batch = the full batch): sums [1],[2],[3] and sets [0] = sum [3] / norm_batch.  One tiny launch, so a
  * sliced step stays free of framework ops inside a captured graph. */
