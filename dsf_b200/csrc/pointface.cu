@@ -254,6 +254,16 @@ face_sort_kernel(int V, int F, const float* __restrict__ verts, const int* __res
 }
 
 #define PF_GROUP 8       // faces per group sphere (PF_CHUNK is a multiple)
+#define PF_SUPER 4       // groups per super-group box
+#define PF_MAXCH 32      // chunk reordering is used up to this many chunks (7 for the MANO mesh)
+
+// squared distance from p to the box a = (lo.xyz, hi.x), b = (hi.y, hi.z)
+__device__ __forceinline__ float box_d2(V3 p, float4 a, float4 b) {
+    const float dx = fmaxf(fmaxf(a.x - p.x, p.x - a.w), 0.f);
+    const float dy = fmaxf(fmaxf(a.y - p.y, p.y - b.x), 0.f);
+    const float dz = fmaxf(fmaxf(a.z - p.z, p.z - b.y), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
 
 // STATS: the same scan, additionally counting per category how many (point, face) pairs were only sphere-tested,
 // evaluated on the interior branch, and evaluated on the edge branch (bench.py's FP32 roofline of config C4)
@@ -263,7 +273,8 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
                       const int* __restrict__ faces, const int* __restrict__ order, const int* __restrict__ face_order,
                       float* __restrict__ dists, int* __restrict__ idxs, unsigned long long* __restrict__ stats) {
     unsigned int n_cull = 0, n_in = 0, n_edge = 0, n_grp = 0;
-    __shared__ float4 s_grp[PF_CHUNK / PF_GROUP];       // bounding sphere of each group of PF_GROUP staged faces
+    __shared__ float4 s_gbox[PF_CHUNK / PF_GROUP][2];   // bounding box of each group of PF_GROUP staged faces
+    __shared__ float4 s_sbox[(PF_CHUNK / PF_GROUP + PF_SUPER - 1) / PF_SUPER][2];   // ... of each PF_SUPER groups
     __shared__ unsigned short s_fid[PF_CHUNK];          // original face id of each staged record
     const int* fo = face_order ? face_order + (size_t)blockIdx.y * F : nullptr;
     __shared__ __align__(16) float s_rec[PF_CHUNK * PF_REC];
@@ -276,9 +287,57 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
     const float* vb = verts + (size_t)b * V * 3;
     float best = INFINITY, sb = INFINITY;          // sb = sqrt(best), refreshed when best improves
     int bi = -1;
-    for (int f0 = 0; f0 < F; f0 += PF_CHUNK) {
-        const int nf = min(PF_CHUNK, F - f0);
+    // Chunk order: faces and points are both in spatial (Morton) order, so the chunk of staged faces whose centroid
+    // is nearest to the centroid of this CTA's 256 points almost always holds every point's nearest face.  Scanning
+    // it first makes `best` tight at once and the later chunks fall to the group test; the minimum and (through the
+    // lowest-index tie rule) the arg-min do not depend on the order.
+    const int n_chunks = (F + PF_CHUNK - 1) / PF_CHUNK;
+    __shared__ float s_cc[PF_MAXCH][3];
+    __shared__ float s_pc[PF_THREADS / 32][4];
+    __shared__ unsigned char s_ord[PF_MAXCH];
+    const bool reorder = fo != nullptr && n_chunks > 1 && n_chunks <= PF_MAXCH;
+    if (reorder) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int c = warp; c < n_chunks; c += PF_THREADS / 32) {
+            const int a0 = c * PF_CHUNK, a1 = min(F, a0 + PF_CHUNK);
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            for (int i = a0 + lane; i < a1; i += 32) {
+                const int fid = fo[i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float* vv = vb + 3 * faces[3 * fid + k];
+                    cx += vv[0]; cy += vv[1]; cz += vv[2];
+                }
+            }
+            cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz);
+            const float inv = 1.f / (3.f * (float)(a1 - a0));
+            if (lane == 0) { s_cc[c][0] = cx * inv; s_cc[c][1] = cy * inv; s_cc[c][2] = cz * inv; }
+        }
+        const float px = warp_sum(live ? p.x : 0.f), py = warp_sum(live ? p.y : 0.f), pz = warp_sum(live ? p.z : 0.f);
+        const float pn = warp_sum(live ? 1.f : 0.f);
+        if (lane == 0) { s_pc[warp][0] = px; s_pc[warp][1] = py; s_pc[warp][2] = pz; s_pc[warp][3] = pn; }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int w = 0; w < PF_THREADS / 32; ++w)
+                for (int k = 0; k < 4; ++k) c[k] += s_pc[w][k];
+            const float inv = c[3] > 0.f ? 1.f / c[3] : 0.f;
+            float d2[PF_MAXCH];
+            for (int k = 0; k < n_chunks; ++k) {
+                const float dx = s_cc[k][0] - c[0] * inv, dy = s_cc[k][1] - c[1] * inv, dz = s_cc[k][2] - c[2] * inv;
+                d2[k] = dx * dx + dy * dy + dz * dz;
+                // insertion sort by distance (comparisons with NaN are false: the result stays a permutation)
+                int q = k;
+                while (q > 0 && d2[s_ord[q - 1]] > d2[k]) { s_ord[q] = s_ord[q - 1]; --q; }
+                s_ord[q] = (unsigned char)k;
+            }
+        }
+        // visibility of s_ord: the __syncthreads() at the top of the chunk loop
+    }
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        __syncthreads();
+        const int f0 = (reorder ? (int)s_ord[ci] : ci) * PF_CHUNK;
+        const int nf = min(PF_CHUNK, F - f0);
         for (int i = threadIdx.x; i < nf; i += PF_THREADS) {
             const int fid = fo ? fo[f0 + i] : f0 + i;
             s_fid[i] = (unsigned short)fid;
@@ -286,35 +345,60 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
         }
         __syncthreads();
         const int ng = (nf + PF_GROUP - 1) / PF_GROUP;
+        const int nsg = (ng + PF_SUPER - 1) / PF_SUPER;
         if (fo) {
-            // group spheres: centre = mean of the members' sphere centres, radius = farthest member sphere surface
-            // (a member that is never culled - radius 1e18 - makes its group unculled as well)
+            // Group boxes: the axis-aligned box of the members' SCALED triangles (see build_face_record: whatever the
+            // full test returns for a face is at least the distance to that triangle, hence to the box), grown by a
+            // rounding margin.  A member that must never be culled (radius 1e18) makes the box infinite.  Boxes of
+            // PF_GROUP faces, then of PF_SUPER groups: Morton-neighbour faces form elongated strips, which boxes fit
+            // far better than spheres, and the test needs no square root of `best`.
             for (int g = threadIdx.x; g < ng; g += PF_THREADS) {
                 const int a0 = g * PF_GROUP, a1 = min(nf, a0 + PF_GROUP);
-                V3 cm = v3(0.f, 0.f, 0.f);
+                float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
                 for (int i = a0; i < a1; ++i) {
                     const float* r = s_rec + i * PF_REC;
-                    cm = cm + v3(r[0] + r[20], r[1] + r[21], r[2] + r[22]);
+                    const float d00 = r[12], d01 = r[13], d11 = r[14];
+                    const float den = d00 * d11 - d01 * d01;
+                    const float k = den > 1e-4f * d00 * d11 && den > 1e-30f ? 1.01f * (den + PF_EPS) / den : INFINITY;
+                    const bool ok = r[23] < 1e18f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float s1 = r[3 + c] * k, s2 = r[6 + c] * k;
+                        const float l = ok ? r[c] + fminf(0.f, fminf(s1, s2)) : -INFINITY;
+                        const float h = ok ? r[c] + fmaxf(0.f, fmaxf(s1, s2)) : INFINITY;
+                        lo[c] = fminf(lo[c], l); hi[c] = fmaxf(hi[c], h);
+                    }
                 }
-                cm = cm * (1.f / (float)(a1 - a0));
-                float rg = 0.f;
-                for (int i = a0; i < a1; ++i) {
-                    const float* r = s_rec + i * PF_REC;
-                    const V3 d = v3(r[0] + r[20], r[1] + r[21], r[2] + r[22]) - cm;
-                    rg = fmaxf(rg, sqrtf(dot(d, d)) + r[23]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float m = 1e-6f * fmaxf(fabsf(lo[c]), fabsf(hi[c])) + 1e-12f;
+                    lo[c] -= m; hi[c] += m;
                 }
-                s_grp[g] = make_float4(cm.x, cm.y, cm.z, rg * 1.0001f + 1e-12f);
+                s_gbox[g][0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+                s_gbox[g][1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+            }
+            __syncthreads();
+            for (int q = threadIdx.x; q < nsg; q += PF_THREADS) {
+                float4 a = s_gbox[q * PF_SUPER][0], b2 = s_gbox[q * PF_SUPER][1];
+                for (int g = q * PF_SUPER + 1; g < min(ng, (q + 1) * PF_SUPER); ++g) {
+                    const float4 c = s_gbox[g][0], d = s_gbox[g][1];
+                    a.x = fminf(a.x, c.x); a.y = fminf(a.y, c.y); a.z = fminf(a.z, c.z); a.w = fmaxf(a.w, c.w);
+                    b2.x = fmaxf(b2.x, d.x); b2.y = fmaxf(b2.y, d.y);
+                }
+                s_sbox[q][0] = a; s_sbox[q][1] = b2;
             }
             __syncthreads();
         }
         for (int g = 0; g < ng; ++g) {
           if (fo) {
-              // one test for the whole group: |p - c_g| > sqrt(best) + r_g implies the same for every member sphere
-              const float4 gs = s_grp[g];
-              const V3 ag = p - v3(gs.x, gs.y, gs.z);
-              const float reach_g = sb + gs.w;
+              // squared distance to the box > best: no member can win (a few 1e-4 of slack against rounding)
+              const float lim = best * 1.0002f + 1e-30f;
+              if (g % PF_SUPER == 0) {
+                  if (STATS && live) ++n_grp;
+                  if (box_d2(p, s_sbox[g / PF_SUPER][0], s_sbox[g / PF_SUPER][1]) > lim) { g += PF_SUPER - 1; continue; }
+              }
               if (STATS && live) ++n_grp;
-              if (dot(ag, ag) > reach_g * reach_g * 1.0002f + 1e-30f) continue;
+              if (box_d2(p, s_gbox[g][0], s_gbox[g][1]) > lim) continue;
           }
           const int fa = g * PF_GROUP, fb = min(nf, fa + PF_GROUP);
           for (int f = fa; f < fb; ++f) {
@@ -367,6 +451,291 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
             if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(stats + k, (unsigned long long)c[k]);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-mesh variant of the forward scan (sorted points + sorted faces, meshes whose records fit shared memory -
+// the MANO mesh: 1554 faces = 149 KB).  One CTA of 1024 threads per hand stages every face record and the box
+// hierarchy ONCE; its 32 warps then pull batches of 32 (spatially neighbouring) points from a shared counter - no
+// chunk loop, no CTA barrier inside the scan, slow batches do not hold the others up.  Inside a warp the work is
+// re-balanced twice, so that every stage runs with (nearly) full warps instead of whichever lanes happen to need it:
+//   stage 1  lane per point, lock step over the super-group / group boxes; a surviving (point, group) pair is
+//            appended to queue A (ballot compaction, no atomics)
+//   stage 2  four pairs of queue A at a time: lane per (point, face of the group) runs the bounding-sphere test with
+//            the owner's point and current bound (shuffles); survivors go to queue B
+//   stage 3  whenever 32 pairs wait in queue B: lane per pair, the full point-triangle evaluation, committed as a
+//            packed (distance bits << 32 | face id) key with a shared-memory atomicMin - the sequential scan's
+//            "lowest face wins ties" rule, independent of the order; every lane then refreshes its bound.
+// The thread-per-point scan evaluated with 7 of 32 lanes active (the evaluation ran whenever any lane needed it).
+// ------------------------------------------------------------------------------------------------
+#define PFA_THREADS 1024
+#define PFA_WARPS (PFA_THREADS / 32)
+#define PFA_QA 136        // queue A: up to 32 lanes x PF_SUPER groups per lock step + 3 waiting
+#define PFA_QB 64         // queue B: up to 32 new pairs per stage-2 step + 31 waiting
+
+struct PfaSmem {
+    float* rec;                    // F * PF_REC
+    float4* gbox;                  // ng * 2
+    float4* sbox;                  // nsg * 2
+    unsigned long long* key;       // PFA_THREADS (32 per warp: the batch in flight)
+    unsigned short* fid;           // F
+    unsigned short* qa;            // warps * PFA_QA  (lane << 8 | group)
+    unsigned short* qb;            // warps * PFA_QB  (lane << 11 | staged face)
+    int* next;                     // batch counter
+};
+
+static size_t pfa_smem_bytes(int F) {
+    const int ng = (F + PF_GROUP - 1) / PF_GROUP, nsg = (ng + PF_SUPER - 1) / PF_SUPER;
+    size_t n = (size_t)F * PF_REC * 4 + (size_t)ng * 32 + (size_t)nsg * 32 + (size_t)PFA_THREADS * 8;
+    n += ((size_t)F * 2 + 15) & ~(size_t)15;
+    n += (size_t)PFA_WARPS * (PFA_QA + PFA_QB) * 2 + 16;
+    return n;
+}
+
+__device__ __forceinline__ PfaSmem pfa_carve(unsigned char* raw, int F) {
+    const int ng = (F + PF_GROUP - 1) / PF_GROUP, nsg = (ng + PF_SUPER - 1) / PF_SUPER;
+    PfaSmem s;
+    s.rec = reinterpret_cast<float*>(raw);
+    s.gbox = reinterpret_cast<float4*>(s.rec + (size_t)F * PF_REC);
+    s.sbox = s.gbox + 2 * ng;
+    s.key = reinterpret_cast<unsigned long long*>(s.sbox + 2 * nsg);
+    s.fid = reinterpret_cast<unsigned short*>(s.key + PFA_THREADS);
+    s.qa = s.fid + (((size_t)F + 7) & ~(size_t)7);
+    s.qb = s.qa + PFA_WARPS * PFA_QA;
+    s.next = reinterpret_cast<int*>(s.qb + PFA_WARPS * PFA_QB);
+    return s;
+}
+
+// full evaluation of (point p, staged record): the sequential scan's arithmetic, unchanged
+template <bool STATS>
+__device__ __forceinline__ float pfa_eval(V3 p, const float* rec, unsigned int* n_in, unsigned int* n_edge) {
+    const float4* r4 = reinterpret_cast<const float4*>(rec);
+    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+    const V3 a = p - v3(q0.x, q0.y, q0.z);
+    const V3 e1 = v3(q0.w, q1.x, q1.y), e2 = v3(q1.z, q1.w, q2.x);
+    const V3 nh = v3(q2.y, q2.z, q2.w);
+    const float t = -dot(a, nh);
+    const V3 c = a + nh * t;
+    const float d20 = dot(c, e1), d21 = dot(c, e2);
+    const float w1 = (q3.z * d20 - q3.y * d21) * q3.w;
+    const float w2 = (q3.x * d21 - q3.y * d20) * q3.w;
+    const float w0 = 1.f - w1 - w2;
+    if (q4.w != 0.f && w0 >= 0.f && w0 <= 1.f && w1 >= 0.f && w1 <= 1.f && w2 >= 0.f && w2 <= 1.f) {
+        if (STATS) ++*n_in;
+        return t * t;
+    }
+    if (STATS) ++*n_edge;
+    const float e01 = seg_d2(a, e1, q4.x);
+    const float e02 = seg_d2(a, e2, q4.y);
+    const float e12 = seg_d2(a - e1, e2 - e1, q4.z);
+    return fminf(fminf(e01, e02), e12);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(PFA_THREADS, 1)
+point_face_fwd_all_kernel(int P, int V, int F, const float* __restrict__ points, const float* __restrict__ verts,
+                          const int* __restrict__ faces, const int* __restrict__ order, const int* __restrict__ face_order,
+                          float* __restrict__ dists, int* __restrict__ idxs, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char pfa_raw[];
+    const PfaSmem s = pfa_carve(pfa_raw, F);
+    unsigned int n_cull = 0, n_in = 0, n_edge = 0, n_grp = 0;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* fo = face_order + (size_t)b * F;
+    const float* vb = verts + (size_t)b * V * 3;
+    const int ng = (F + PF_GROUP - 1) / PF_GROUP, nsg = (ng + PF_SUPER - 1) / PF_SUPER;
+    for (int i = tid; i < F; i += PFA_THREADS) {
+        const int fid = fo[i];
+        s.fid[i] = (unsigned short)fid;
+        build_face_record(vb, faces, fid, s.rec + (size_t)i * PF_REC);
+    }
+    if (tid == 0) *s.next = 0;
+    __syncthreads();
+    // group / super-group boxes: see point_face_fwd_kernel
+    for (int g = tid; g < ng; g += PFA_THREADS) {
+        const int a0 = g * PF_GROUP, a1 = min(F, a0 + PF_GROUP);
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = a0; i < a1; ++i) {
+            const float* r = s.rec + (size_t)i * PF_REC;
+            const float d00 = r[12], d01 = r[13], d11 = r[14];
+            const float den = d00 * d11 - d01 * d01;
+            const float k = den > 1e-4f * d00 * d11 && den > 1e-30f ? 1.01f * (den + PF_EPS) / den : INFINITY;
+            const bool ok = r[23] < 1e18f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float s1 = r[3 + c] * k, s2 = r[6 + c] * k;
+                const float l = ok ? r[c] + fminf(0.f, fminf(s1, s2)) : -INFINITY;
+                const float h = ok ? r[c] + fmaxf(0.f, fmaxf(s1, s2)) : INFINITY;
+                lo[c] = fminf(lo[c], l); hi[c] = fmaxf(hi[c], h);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float m = 1e-6f * fmaxf(fabsf(lo[c]), fabsf(hi[c])) + 1e-12f;
+            lo[c] -= m; hi[c] += m;
+        }
+        s.gbox[2 * g] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+        s.gbox[2 * g + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int q = tid; q < nsg; q += PFA_THREADS) {
+        float4 a = s.gbox[2 * q * PF_SUPER], b2 = s.gbox[2 * q * PF_SUPER + 1];
+        for (int g = q * PF_SUPER + 1; g < min(ng, (q + 1) * PF_SUPER); ++g) {
+            const float4 c = s.gbox[2 * g], d = s.gbox[2 * g + 1];
+            a.x = fminf(a.x, c.x); a.y = fminf(a.y, c.y); a.z = fminf(a.z, c.z); a.w = fmaxf(a.w, c.w);
+            b2.x = fmaxf(b2.x, d.x); b2.y = fmaxf(b2.y, d.y);
+        }
+        s.sbox[2 * q] = a; s.sbox[2 * q + 1] = b2;
+    }
+    __syncthreads();
+    // ---- from here on the warps run independently (warp-level synchronisation only)
+    unsigned short* qa = s.qa + warp * PFA_QA;
+    unsigned short* qb = s.qb + warp * PFA_QB;
+    unsigned long long* wkey = s.key + (warp << 5);
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int n_batches = (P + 31) >> 5;
+    for (;;) {
+        int wb = 0;
+        if (lane == 0) wb = blockIdx.x + gridDim.x * atomicAdd(s.next, 1);
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        if (wb >= n_batches) break;
+        const int slot = (wb << 5) + lane;
+        const bool live = slot < P;
+        const int pi = live ? order[(size_t)b * P + slot] : 0;
+        const float* pp = points + ((size_t)b * P + pi) * 3;
+        const V3 p = v3(pp[0], pp[1], pp[2]);
+        wkey[lane] = ((unsigned long long)__float_as_uint(INFINITY) << 32) | 0xffffffffull;
+        float best = INFINITY, sb = INFINITY;
+        int nA = 0, nB = 0;                                   // queue fill levels (warp-uniform registers)
+        __syncwarp();
+        // stage 3: evaluate everything waiting in queue B
+        auto flush_b = [&]() {
+            __syncwarp();
+            for (int i0 = 0; i0 < nB; i0 += 32) {
+                const int i = i0 + lane;
+                const unsigned int e = i < nB ? qb[i] : 0u;
+                const int owner = (int)(e >> 11), f = (int)(e & 2047u);
+                const V3 q = v3(__shfl_sync(0xffffffffu, p.x, owner), __shfl_sync(0xffffffffu, p.y, owner),
+                                __shfl_sync(0xffffffffu, p.z, owner));
+                if (i < nB) {
+                    const float d = pfa_eval<STATS>(q, s.rec + (size_t)f * PF_REC, &n_in, &n_edge);
+                    atomicMin(wkey + owner, ((unsigned long long)__float_as_uint(d) << 32) | s.fid[f]);
+                }
+            }
+            nB = 0;
+            __syncwarp();
+            best = __uint_as_float((unsigned int)(wkey[lane] >> 32));
+            sb = sqrtf(best);
+        };
+        // stage 2: `take` (<= 4) pairs from the top of queue A, lane per (pair, face of its group)
+        auto sphere_step = [&](int take) {
+            nA -= take;
+            const int j = lane >> 3;
+            const unsigned int e = j < take ? qa[nA + j] : 0u;
+            const int owner = (int)(e >> 8), f = (int)(e & 255u) * PF_GROUP + (lane & 7);
+            const V3 q = v3(__shfl_sync(0xffffffffu, p.x, owner), __shfl_sync(0xffffffffu, p.y, owner),
+                            __shfl_sync(0xffffffffu, p.z, owner));
+            const float sbo = __shfl_sync(0xffffffffu, sb, owner);
+            bool pass = false;
+            if (j < take && f < F) {
+                const float4* r4 = reinterpret_cast<const float4*>(s.rec + (size_t)f * PF_REC);
+                const float4 q0 = r4[0], q5 = r4[5];
+                const V3 ac = q - v3(q0.x, q0.y, q0.z) - v3(q5.x, q5.y, q5.z);
+                const float reach = sbo + q5.w;
+                pass = !(dot(ac, ac) > reach * reach * 1.0002f + 1e-30f);
+                if (STATS && !pass) ++n_cull;
+            }
+            const unsigned int mk = __ballot_sync(0xffffffffu, pass);
+            if (pass) qb[nB + __popc(mk & lt_mask)] = (unsigned short)((owner << 11) | f);
+            nB += __popc(mk);
+            if (nB >= 32) flush_b();
+        };
+        // start with the super-group nearest to the batch: the first evaluations then give every lane a tight bound
+        int start = 0;
+        {
+            const float wn = warp_sum(live ? 1.f : 0.f);
+            const float inv = wn > 0.f ? 1.f / wn : 0.f;
+            const V3 c = v3(warp_sum(live ? p.x : 0.f) * inv, warp_sum(live ? p.y : 0.f) * inv, warp_sum(live ? p.z : 0.f) * inv);
+            float dmin = INFINITY;
+            int imin = 0;
+            for (int q = lane; q < nsg; q += 32) {
+                const float d = box_d2(c, s.sbox[2 * q], s.sbox[2 * q + 1]);
+                if (d < dmin) { dmin = d; imin = q; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float d2 = __shfl_xor_sync(0xffffffffu, dmin, o);
+                const int i2 = __shfl_xor_sync(0xffffffffu, imin, o);
+                if (d2 < dmin || (d2 == dmin && i2 < imin)) { dmin = d2; imin = i2; }
+            }
+            start = imin;
+        }
+        // stage 1: lock step over the boxes
+        for (int k = 0; k < nsg; ++k) {
+            int q = start + k;
+            if (q >= nsg) q -= nsg;
+            if (STATS && live) ++n_grp;
+            const bool want = live && !(box_d2(p, s.sbox[2 * q], s.sbox[2 * q + 1]) > best * 1.0002f + 1e-30f);
+            if (!__any_sync(0xffffffffu, want)) continue;
+            const int g1 = min(ng, (q + 1) * PF_SUPER);
+            for (int g = q * PF_SUPER; g < g1; ++g) {
+                bool in_g = want;
+                if (in_g) {
+                    if (STATS) ++n_grp;
+                    in_g = !(box_d2(p, s.gbox[2 * g], s.gbox[2 * g + 1]) > best * 1.0002f + 1e-30f);
+                }
+                const unsigned int mk = __ballot_sync(0xffffffffu, in_g);
+                if (in_g) qa[nA + __popc(mk & lt_mask)] = (unsigned short)((lane << 8) | g);
+                nA += __popc(mk);
+            }
+            __syncwarp();
+            while (nA >= 4) { sphere_step(4); __syncwarp(); }
+        }
+        while (nA > 0) { sphere_step(min(4, nA)); __syncwarp(); }
+        flush_b();
+        if (live) {
+            const unsigned long long kk = wkey[lane];
+            dists[(size_t)b * P + pi] = __uint_as_float((unsigned int)(kk >> 32));
+            idxs[(size_t)b * P + pi] = (int)(unsigned int)(kk & 0xffffffffull);
+        }
+        __syncwarp();
+    }
+    if (STATS) {
+        unsigned int c[4] = {n_cull, n_in, n_edge, n_grp};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+            if (lane == 0 && c[k]) atomicAdd(stats + k, (unsigned long long)c[k]);
+        }
+    }
+}
+
+// launch the forward scan: whole-mesh kernel when the points and faces are sorted and the records fit shared memory
+template <bool STATS>
+static int launch_point_face_fwd(int batch, int P, int V, int F, const float* points, const float* verts, const int* faces,
+                                 const int* order, const int* face_order, float* dists, int* idxs,
+                                 unsigned long long* stats, cudaStream_t st) {
+    const size_t smem = pfa_smem_bytes(F);
+    if (order && face_order && F <= 2047 && smem <= 220 * 1024 && P >= 512) {
+        static bool attr_set[16][2] = {};
+        int dev = 0;
+        DSF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 16 || !attr_set[dev][STATS]) {
+            DSF_CHECK_CUDA(cudaFuncSetAttribute(point_face_fwd_all_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                220 * 1024));
+            if (dev < 16) attr_set[dev][STATS] = true;
+        }
+        // one CTA per hand; small batches split every hand's point batches over two CTAs to fill the chip
+        dim3 grid(batch < 148 ? 2 : 1, batch);
+        point_face_fwd_all_kernel<STATS><<<grid, PFA_THREADS, smem, st>>>(P, V, F, points, verts, faces, order, face_order,
+                                                                        dists, idxs, stats);
+    } else {
+        dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
+        point_face_fwd_kernel<STATS><<<grid, PF_THREADS, 0, st>>>(P, V, F, points, verts, faces, order, face_order, dists,
+                                                                idxs, stats);
+    }
+    DSF_CHECK_LAUNCH();
+    return DSF_OK;
 }
 
 __device__ __forceinline__ void atomic_add3(float* dst, V3 g) {
@@ -457,11 +826,8 @@ extern "C" int dsf_point_face_forward(int batch, int P, int V, int F, const floa
         face_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(V, F, verts, faces, face_order);
         DSF_CHECK_LAUNCH();
     }
-    dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
-    point_face_fwd_kernel<false><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
-                                                                              face_order, dists, idxs, nullptr);
-    DSF_CHECK_LAUNCH();
-    return DSF_OK;
+    return launch_point_face_fwd<false>(batch, P, V, F, points, verts, faces, order_ws, face_order, dists, idxs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 // Work counters of the forward scan for the same inputs: stats[0] = pairs rejected by their own bounding-sphere
@@ -486,11 +852,8 @@ extern "C" int dsf_point_face_stats(int batch, int P, int V, int F, const float*
         face_sort_kernel<<<batch, PS_THREADS, 0, (cudaStream_t)stream>>>(V, F, verts, faces, face_order);
         DSF_CHECK_LAUNCH();
     }
-    dim3 grid((P + PF_THREADS - 1) / PF_THREADS, batch);
-    point_face_fwd_kernel<true><<<grid, PF_THREADS, 0, (cudaStream_t)stream>>>(P, V, F, points, verts, faces, order_ws,
-                                                                             face_order, dists, idxs, stats);
-    DSF_CHECK_LAUNCH();
-    return DSF_OK;
+    return launch_point_face_fwd<true>(batch, P, V, F, points, verts, faces, order_ws, face_order, dists, idxs, stats,
+                                       (cudaStream_t)stream);
 }
 
 extern "C" int dsf_point_face_backward(int batch, int P, int V, int F, const float* points, const float* verts,
