@@ -590,7 +590,8 @@ point_face_fwd_all_kernel(int P, int V, int F, const float* __restrict__ points,
     // ---- from here on the warps run independently (warp-level synchronisation only)
     unsigned short* qa = s.qa + warp * PFA_QA;
     unsigned short* qb = s.qb + warp * PFA_QB;
-    unsigned long long* wkey = s.key + (warp << 5);
+    unsigned int* wd = reinterpret_cast<unsigned int*>(s.key) + (warp << 6);      // 32 distance bit patterns ...
+    unsigned int* wf = wd + 32;                                                     // ... and 32 face ids per warp
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int n_batches = (P + 31) >> 5;
     for (;;) {
@@ -603,7 +604,8 @@ point_face_fwd_all_kernel(int P, int V, int F, const float* __restrict__ points,
         const int pi = live ? order[(size_t)b * P + slot] : 0;
         const float* pp = points + ((size_t)b * P + pi) * 3;
         const V3 p = v3(pp[0], pp[1], pp[2]);
-        wkey[lane] = ((unsigned long long)__float_as_uint(INFINITY) << 32) | 0xffffffffull;
+        wd[lane] = __float_as_uint(INFINITY);
+        wf[lane] = 0xffffffffu;
         float best = INFINITY, sb = INFINITY;
         int nA = 0, nB = 0;                                   // queue fill levels (warp-uniform registers)
         __syncwarp();
@@ -616,14 +618,23 @@ point_face_fwd_all_kernel(int P, int V, int F, const float* __restrict__ points,
                 const int owner = (int)(e >> 11), f = (int)(e & 2047u);
                 const V3 q = v3(__shfl_sync(0xffffffffu, p.x, owner), __shfl_sync(0xffffffffu, p.y, owner),
                                 __shfl_sync(0xffffffffu, p.z, owner));
+                // commit min (distance, face id) per owner with native 32-bit atomics (a 64-bit atomicMin on shared
+                // memory is a compare-and-swap loop, and the pairs of one owner sit next to each other): distances
+                // first; an owner whose distance improved forgets its face; then the faces of the pairs that hold
+                // their owner's minimum.  NaN distances (bit pattern above +inf) never win, as in the sequential scan.
+                unsigned int dbits = 0xffffffffu;
                 if (i < nB) {
-                    const float d = pfa_eval<STATS>(q, s.rec + (size_t)f * PF_REC, &n_in, &n_edge);
-                    atomicMin(wkey + owner, ((unsigned long long)__float_as_uint(d) << 32) | s.fid[f]);
+                    dbits = __float_as_uint(pfa_eval<STATS>(q, s.rec + (size_t)f * PF_REC, &n_in, &n_edge));
+                    if (dbits < 0x7f800000u) atomicMin(wd + owner, dbits);     // +inf / NaN never win (bi stays -1)
                 }
+                __syncwarp();
+                const unsigned int mine = wd[lane];
+                if (mine < __float_as_uint(best)) { best = __uint_as_float(mine); wf[lane] = 0xffffffffu; }
+                __syncwarp();
+                if (i < nB && dbits < 0x7f800000u && dbits == wd[owner]) atomicMin(wf + owner, (unsigned int)s.fid[f]);
+                __syncwarp();
             }
             nB = 0;
-            __syncwarp();
-            best = __uint_as_float((unsigned int)(wkey[lane] >> 32));
             sb = sqrtf(best);
         };
         // stage 2: `take` (<= 4) pairs from the top of queue A, lane per (pair, face of its group)
@@ -693,9 +704,8 @@ point_face_fwd_all_kernel(int P, int V, int F, const float* __restrict__ points,
         while (nA > 0) { sphere_step(min(4, nA)); __syncwarp(); }
         flush_b();
         if (live) {
-            const unsigned long long kk = wkey[lane];
-            dists[(size_t)b * P + pi] = __uint_as_float((unsigned int)(kk >> 32));
-            idxs[(size_t)b * P + pi] = (int)(unsigned int)(kk & 0xffffffffull);
+            dists[(size_t)b * P + pi] = __uint_as_float(wd[lane]);
+            idxs[(size_t)b * P + pi] = (int)wf[lane];
         }
         __syncwarp();
     }
