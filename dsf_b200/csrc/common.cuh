@@ -73,6 +73,7 @@ struct DsfMano {
 struct ChainTopo {
     int parents[NJ];
     int level[NJ];
+    int nchild[NJ];     // number of children of each joint
     int maxlevel;
 };
 

@@ -258,7 +258,10 @@ static ChainTopo topo_of(const DsfMano* h) {
     for (int i = 0; i < NJ; ++i) {
         t.parents[i] = h->parents[i];
         t.level[i] = h->level[i];
+        t.nchild[i] = 0;
     }
+    for (int i = 1; i < NJ; ++i)
+        if (h->parents[i] >= 0 && h->parents[i] < NJ) ++t.nchild[h->parents[i]];
     t.maxlevel = h->maxlevel;
     return t;
 }
@@ -726,18 +729,30 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
             float up[9];
             mat3_mulT(gGr, R, up);                       // g_Gr_p += g_Gr_j R_j^T + g_Gt_j (x) d
             float* pacc = s_acc[hl][pj];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) atomicAdd(&pacc[3 * r + c], up[3 * r + c] + gGt[r] * d[c]);
             float gd[3];
             mat3T_vec(Pg, gGt, gd);
+            if (topo.nchild[pj] == 1) {
+                // the only child of its parent (every finger joint but the first): nobody else touches the parent's
+                // cotangent at this level - plain adds instead of shared-memory float atomics (compare-and-swap loops)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                atomicAdd(&pacc[9 + e], gGt[e]);
-                atomicAdd(&pacc[12 + e], -gd[e]);
-                atomicAdd(&acc[12 + e], gd[e]);
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) pacc[3 * r + c] += up[3 * r + c] + gGt[r] * d[c];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { pacc[9 + e] += gGt[e]; pacc[12 + e] -= gd[e]; }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(&pacc[3 * r + c], up[3 * r + c] + gGt[r] * d[c]);
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    atomicAdd(&pacc[9 + e], gGt[e]);
+                    atomicAdd(&pacc[12 + e], -gd[e]);
+                }
             }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) acc[12 + e] += gd[e];        // own slot
         }
         __syncwarp();
     }
@@ -749,12 +764,14 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     // pose blend shapes: pose_feature = Rs - I
     if (j >= 1) {
         const float* gx = wsh + WS_GX + 10 + 9 * (j - 1);
+        float a9[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) {
-            float a = 0.f;
-            for (int z = 0; z < n_split; ++z) a += gx[z * KP + e];     // fixed order: deterministic
-            gR[e] += a;
-        }
+        for (int e = 0; e < 9; ++e) a9[e] = 0.f;
+        for (int z = 0; z < n_split; ++z)                              // fixed order: deterministic; nine independent
+#pragma unroll
+            for (int e = 0; e < 9; ++e) a9[e] += gx[z * KP + e];       // loads in flight per split
+#pragma unroll
+        for (int e = 0; e < 9; ++e) gR[e] += a9[e];
     }
     __syncwarp();
     if (j == 0 && p.quat_dim == 4) {
