@@ -532,31 +532,47 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
     const float* gv = g_verts ? g_verts + (size_t)hand * NVW * 3 : nullptr;
     const float* vo = verts + (size_t)hand * NVW * 3;
     // vertex cotangent straight from the rasteriser's per-tile shares (fused step): sum the tiles, apply the
-    // hand's loss normalisation gk / zhalf
-    const float gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
-    // the flagged tiles of this hand, resolved once (at most 8 tiles are walked through registers; more fall back)
-    const float* tile_ptr[8];
-    int n_live_tiles = 0;
-    if (gt.gv_tile && gt.n_tiles <= 8)
-        for (int t = 0; t < gt.n_tiles; ++t)
-            if (gt.gv_flag[(size_t)hand * gt.n_tiles + t])
-                tile_ptr[n_live_tiles++] = gt.gv_tile + ((size_t)hand * gt.n_tiles + t) * NVW * 3;
-    if (lf.parts && lf.n_mesh == B && tid == 0) {            // per-hand loss record = sum of its tiles
-        float a = 0.f, c = 0.f;
-        for (int t = 0; t < lf.n_tiles; ++t) {
-            a += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2];
-            c += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2 + 1];
+    // hand's loss normalisation gk / zhalf.  The hand-level values (normalisation, which tiles carry a gradient,
+    // the loss record) are worked out once, by thread 0, not by every thread.
+    __shared__ float s_gts;
+    __shared__ int s_live[9];                 // [0] = number of live tiles (-1: more than 8 tiles, general path), then ids
+    if (tid == 0) {
+        s_gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
+        int n_live = -1;
+        if (gt.gv_tile && gt.n_tiles <= 8) {
+            n_live = 0;
+            for (int t = 0; t < gt.n_tiles; ++t)
+                if (gt.gv_flag[(size_t)hand * gt.n_tiles + t]) s_live[1 + n_live++] = t;
         }
-        lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
+        s_live[0] = n_live;
+        if (lf.parts && lf.n_mesh == B) {                   // per-hand loss record = sum of its tiles
+            float a = 0.f, c = 0.f;
+            for (int t = 0; t < lf.n_tiles; ++t) {
+                a += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2];
+                c += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2 + 1];
+            }
+            lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
+        }
     }
+    __syncthreads();
+    const float gts = s_gts;
+    const int n_live_tiles = s_live[0];
+    const float* tile0 = nullptr;
+    const float* tile1 = nullptr;
+    if (n_live_tiles >= 1) tile0 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[1]) * NVW * 3;
+    if (n_live_tiles >= 2) tile1 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[2]) * NVW * 3;
     for (int v = tid; v < NVW; v += SKB_T) {
         float a = gv ? gv[3 * v] : 0.f, b = gv ? gv[3 * v + 1] : 0.f, c = gv ? gv[3 * v + 2] : 0.f;
         if (gt.gv_tile) {
-            if (gt.n_tiles <= 8) {
+            if (n_live_tiles >= 0) {
                 a = b = c = 0.f;
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (t < n_live_tiles) { a += tile_ptr[t][3 * v]; b += tile_ptr[t][3 * v + 1]; c += tile_ptr[t][3 * v + 2]; }
+                // ascending tile order (fixed summation order); one or two live tiles is the 128 x 128 crop
+                if (tile0) { a += tile0[3 * v]; b += tile0[3 * v + 1]; c += tile0[3 * v + 2]; }
+                if (tile1) { a += tile1[3 * v]; b += tile1[3 * v + 1]; c += tile1[3 * v + 2]; }
+                for (int t = 2; t < n_live_tiles; ++t) {
+                    const float* tp = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[1 + t]) * NVW * 3;
+                    a += tp[3 * v]; b += tp[3 * v + 1]; c += tp[3 * v + 2];
+                }
                 a *= gts; b *= gts; c *= gts;
             } else {
                 a = gts * grad_tiles_load(gt, hand, 3 * v);
