@@ -499,6 +499,7 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const int* __restrict__ wv
 //   cotangents of verts/joints -> g_vposed (ws), g_A (ws), g_cam.
 // ------------------------------------------------------------------------------------------------
 #define SKB_T 256
+#define SKB_TILE_BYTES ((NVW * 3 * 4 + 15 + 15) & ~15)      // a 9348-byte row plus its alignment window
 
 __global__ void __launch_bounds__(SKB_T)
 mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_ptr, const int2* __restrict__ wv_ent,
@@ -511,12 +512,52 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
                      float* __restrict__ g_cam, int ld_gcam, GradTiles gt, const float* __restrict__ cube,
                      LossFold lf) {
     __shared__ float sg[NVW * 3];
-    __shared__ float svp[NV * 3];
+    __shared__ __align__(16) float svp[NP];                  // v_posed of the hand (padded row of the workspace)
+    __shared__ __align__(16) unsigned char s_tiles[2][SKB_TILE_BYTES];   // the rasteriser's two gradient shares
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ float sGr[NJ][9];
     __shared__ float sgj[NJOUT * 3];
     __shared__ float red[SKB_T / 32][12];
     const int hand = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     float* wsh = ws + (size_t)hand * WS_PER_HAND;
+    // Bulk staging (fused step at crop sizes up to 128, i.e. at most two raster tiles per hand): one thread hands the
+    // hand's v_posed row and both per-tile gradient shares (28 KB) to the TMA engine before anything else happens, so
+    // the copies fly while the CTA resolves the hand-level scalars - instead of every thread walking three global
+    // arrays with stride-12-byte loads whose latency nothing covers.  The shares' rows are 9348 bytes apart (not a
+    // multiple of 16): each copy takes the 16-byte aligned window around its row, the data starts `shift` bytes in.
+    const bool bulk = gt.gv_tile != nullptr && gt.n_tiles <= 2 && ((reinterpret_cast<uintptr_t>(wsh + WS_VP) & 15) == 0);
+    uint32_t t_shift[2] = {0u, 0u};
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        uint32_t t_bytes[2] = {0u, 0u};
+        const char* t_src[2] = {nullptr, nullptr};
+        uint32_t total = NP * (uint32_t)sizeof(float);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (t < gt.n_tiles) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(gt.gv_tile + ((size_t)hand * gt.n_tiles + t) * NVW * 3);
+                t_shift[t] = (uint32_t)(a & 15);
+                t_bytes[t] = (t_shift[t] + NVW * 3 * (uint32_t)sizeof(float) + 15u) & ~15u;
+                t_src[t] = reinterpret_cast<const char*>(a - t_shift[t]);
+                total += t_bytes[t];
+            }
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(svp)),
+                         "l"(wsh + WS_VP), "r"(NP * (uint32_t)sizeof(float)), "r"(bar)
+                         : "memory");
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (t < gt.n_tiles)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     (uint32_t)__cvta_generic_to_shared(s_tiles[t])),
+                                 "l"(t_src[t]), "r"(t_bytes[t]), "r"(bar)
+                                 : "memory");
+        }
+    }
     float cs = 1.f, tx = 0.f, ty = 0.f, tz = 0.f;
     if (cam) {
         cs = cam[(size_t)hand * ld_cam];
@@ -554,13 +595,22 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
             lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
         }
     }
-    __syncthreads();
+    __syncthreads();                          // also: the mbarrier is initialised before anyone polls it
     const float gts = s_gts;
     const int n_live_tiles = s_live[0];
     const float* tile0 = nullptr;
     const float* tile1 = nullptr;
-    if (n_live_tiles >= 1) tile0 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[1]) * NVW * 3;
-    if (n_live_tiles >= 2) tile1 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[2]) * NVW * 3;
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n" ::"r"(bar)
+            : "memory");
+        if (n_live_tiles >= 1) tile0 = reinterpret_cast<const float*>(s_tiles[s_live[1]] + t_shift[s_live[1]]);
+        if (n_live_tiles >= 2) tile1 = reinterpret_cast<const float*>(s_tiles[s_live[2]] + t_shift[s_live[2]]);
+    } else {
+        if (n_live_tiles >= 1) tile0 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[1]) * NVW * 3;
+        if (n_live_tiles >= 2) tile1 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[2]) * NVW * 3;
+    }
     for (int v = tid; v < NVW; v += SKB_T) {
         float a = gv ? gv[3 * v] : 0.f, b = gv ? gv[3 * v + 1] : 0.f, c = gv ? gv[3 * v + 2] : 0.f;
         if (gt.gv_tile) {
@@ -625,7 +675,7 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
     for (int v = tid; v < NV; v += SKB_T) {
         const float g0 = sg[3 * v] * s_tot, g1 = sg[3 * v + 1] * s_tot, g2 = sg[3 * v + 2] * s_tot;
         sg[3 * v] = g0; sg[3 * v + 1] = g1; sg[3 * v + 2] = g2;
-        svp[3 * v] = VP[3 * v]; svp[3 * v + 1] = VP[3 * v + 1]; svp[3 * v + 2] = VP[3 * v + 2];
+        if (!bulk) { svp[3 * v] = VP[3 * v]; svp[3 * v + 1] = VP[3 * v + 1]; svp[3 * v + 2] = VP[3 * v + 2]; }
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
