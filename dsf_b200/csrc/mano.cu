@@ -424,9 +424,22 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const int* __restrict__ wv
                  float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ Rs) {
     __shared__ float sA[NJ][12];
     __shared__ float sV[NVW * 3];
+    __shared__ __align__(16) float sVP[NP];                  // v_posed row, staged by one TMA bulk copy
+    __shared__ __align__(8) unsigned long long s_bar;
     const int hand = blockIdx.x;
     const int tid = threadIdx.x;
     const float* wsh = ws + (size_t)hand * WS_PER_HAND;
+    const bool bulk = (reinterpret_cast<uintptr_t>(wsh + WS_VP) & 15) == 0;
+    if (bulk && tid == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NP * (uint32_t)sizeof(float)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(sVP)),
+                     "l"(wsh + WS_VP), "r"(NP * (uint32_t)sizeof(float)), "r"(bar)
+                     : "memory");
+    }
     for (int i = tid; i < NJ * 12; i += SKIN_T) {
         int j = i / 12, e = i % 12;
         sA[j][e] = (e < 9) ? wsh[WS_RJ + j * RJ_STRIDE + RJ_GR + e] : wsh[WS_RJ + j * RJ_STRIDE + RJ_AT + e - 9];
@@ -442,8 +455,15 @@ mano_skin_kernel(int B, const float* __restrict__ ws, const int* __restrict__ wv
         ty = cam[(size_t)hand * ld_cam + 2];
         tz = cam[(size_t)hand * ld_cam + 3];
     }
-    __syncthreads();
+    __syncthreads();                          // sA complete; the mbarrier is initialised before anyone polls it
     const float* VP = wsh + WS_VP;
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n" ::"r"(bar)
+            : "memory");
+        VP = sVP;
+    }
     float* vo = verts + (size_t)hand * NVW * 3;
     for (int v = tid; v < NV; v += SKIN_T) {
         float x = VP[3 * v], y = VP[3 * v + 1], z = VP[3 * v + 2];
