@@ -750,7 +750,39 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         }
     }
     flush_cands();                                            // ---------------- phase C (remainder)
-    __syncthreads();
+    // Every warp prepares its own, now dead, candidate-list region for the epilogue BEFORE it waits for the others
+    // (the epilogue's tables live in those regions, see below): zero fill = the face moments, the fixed-point vertex
+    // sums and the gradient maxima start at zero; warp 0 also owns the words of the crop box and of the pixel-index
+    // tables.  Work a warp does while the stragglers of the face loop finish is free, and the epilogue needs no
+    // barrier of its own before the pixel passes.  (Scoped: nothing here stays live across the barrier.)
+    {
+        const bool has_t = target != nullptr || (ROWS && trows.rows != nullptr);
+        const bool grad_pre = !PERSP && tail.gv_tile != nullptr && has_t;
+        if (grad_pre) {
+            uint4* z4 = reinterpret_cast<uint4*>(my_cands);
+            for (int i = lane; i < RT_WCANDS / 4; i += 32) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+        }
+        if (warp == 0) {
+            if (has_t && crop.joints) crop_box_warp(crop, mesh, place_off, place_scale, lane, reinterpret_cast<CropBox*>(s.cands));
+            if (grad_pre) {
+                int* qx_ = reinterpret_cast<int*>(s.cands + 96);
+                int* qy_ = qx_ + RT_TW;
+                const int tw_ = tx1 - tx0 + 1, th_ = ty1 - ty0 + 1;
+                const float cx = s.xs[tx0], cy = s.ys[ty0];
+                const int q0x_ = (cx == cx) ? __float2int_rn(((1.f - cx) * vw.S - 1.f) * 0.5f) : 0;
+                const int q0y_ = (cy == cy) ? __float2int_rn(((1.f - cy) * vw.S - 1.f) * 0.5f) : 0;
+                for (int i = lane; i < tw_ + th_; i += 32) {
+                    const bool isx = i < tw_;
+                    const float c = isx ? s.xs[tx0 + i] : s.ys[ty0 + i - tw_];
+                    const int q = (c == c) ? __float2int_rn(((1.f - c) * vw.S - 1.f) * 0.5f) : 0;
+                    if (isx) qx_[i] = q - q0x_; else qy_[i - tw_] = q - q0y_;
+                }
+            }
+        }
+    }
+    __syncthreads();                                          // z-buffer complete, epilogue tables ready
+
 
     // epilogue: background fill (:1084-1085) + normalize_img (:1289-1299); with a target image the
     // m2d loss partial sums of this tile (train_render.py:728-731) are produced on the way out
@@ -785,22 +817,9 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
     // (it needs the mask count of all tiles).  No pix_to_face plane, no second pass over target / img, no backward
     // kernel, bit-reproducible.
     const bool do_grad = !PERSP && tail.gv_tile != nullptr && has_target;
-    if (do_crop && tid < 32) crop_box_warp(crop, mesh, place_off, place_scale, tid, cbox);
     const float cx0s = s.xs[tx0], cy0s = s.ys[ty0];
     const int q0x = (cx0s == cx0s) ? __float2int_rn(((1.f - cx0s) * vw.S - 1.f) * 0.5f) : 0;
     const int q0y = (cy0s == cy0s) ? __float2int_rn(((1.f - cy0s) * vw.S - 1.f) * 0.5f) : 0;
-    if (do_grad) {
-        for (int i = tid; i < 3 * Fp; i += RT_THREADS) mom[i] = 0;
-        for (int i = tid; i < NVW * 3; i += RT_THREADS) sgn[i] = 0;
-        if (tid < 2) s_gmax[tid] = 0;
-        for (int i = tid; i < tw + th; i += RT_THREADS) {
-            const bool isx = i < tw;
-            const float c = isx ? s.xs[tx0 + i] : s.ys[ty0 + i - tw];
-            const int q = (c == c) ? __float2int_rn(((1.f - c) * vw.S - 1.f) * 0.5f) : 0;
-            if (isx) qx[i] = q - q0x; else qy[i - tw] = q - q0y;
-        }
-    }
-    if (do_crop || do_grad) __syncthreads();
     auto add_moments = [&](int f, int n, int mi, int dqy) {
         if (f >= 0 && (n | mi) != 0) {
             if (n) { atomicAdd(&mom[3 * f], n); atomicAdd(&mom[3 * f + 2], n * dqy); }
