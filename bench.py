@@ -249,20 +249,20 @@ class L2Flusher:
 
 def timed_steps(fn, steps, flush=None):
     """ms per step on the device: back to back when the working set exceeds L2, else one event pair per step
-    with an L2 flush (outside the events) in between."""
+    with an L2 flush (outside the events) in between.  The flush, the event records and the step are enqueued
+    back to back (no host synchronisation inside the loop): the flush kernel runs while the host enqueues the
+    step behind it, so the event pair brackets the step's device time and not the host's launch latency."""
     if flush is None:
         return time_region(fn, steps)
-    total = 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for e0, e1 in ev:
         flush()
-        torch.cuda.synchronize()
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        total += e0.elapsed_time(e1)
-    return total / steps
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps
 
 
 def run_ours(args):
