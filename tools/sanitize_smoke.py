@@ -28,6 +28,15 @@ for R in (128, 100):
     s.step()
     torch.cuda.synchronize()
     print("fit step R", R, "loss", float(s.totals[0]))
+from dsf_b200.pcl import pack_target_rows
+s = FitStep(layer, B, 128, use_graph=False, chunks=2, keep_pix_to_face=False, fuse_target_rows=True)
+s.set_inputs(inp["params"], inp["center3d"], inp["cube"])
+s.render_target(inp["params_target"])
+mm = quantise_depth_mm(s.target, s.center3d, s.cube)
+s.set_inputs(inp["params"], inp["center3d"], inp["cube"], pack_target_rows(mm.cpu(), inp["center3d"].cpu(), inp["cube"].cpu()))
+s.step()                                                   # row-run target decoded in the raster epilogue, two slices
+torch.cuda.synchronize()
+print("fit step rows", float(s.totals[0]))
 s = FitStep(layer, B, 128, use_graph=False)
 s.set_inputs(inp["params"], inp["center3d"], inp["cube"])
 s.render_target(inp["params_target"])
@@ -43,7 +52,8 @@ v, j = layer.get_mano_vertices(p[:, :3], p[:, 3:48], p[:, 48:58], p[:, 58:], glo
 jg = j.detach().requires_grad_(True)
 layer.calculate_coll(jg, v.detach()).backward()
 vg = v.detach().requires_grad_(True)
-ICPLoss(vg, pcl[:, :512].contiguous(), layer.faces).mean().backward()
+ICPLoss(vg, pcl[:, :512].contiguous(), layer.faces).mean().backward()      # whole-mesh point-face kernel (P >= 512)
+ICPLoss(vg, pcl[:, :300].contiguous(), layer.faces).mean().backward()      # chunked point-face kernel
 seg = layer.seg_pcl(j.detach(), j.detach(), v.detach(), pcl[:, :256].contiguous())
 v_mm = layer.get_mano_vertices(p[:, :3], p[:, 3:48] * 3, p[:, 48:58], p[:, 58:])[0].detach()
 iv = intersect_counts(v_mm[:2].contiguous(), PartTopology.synthetic_hand(), 2.0)
