@@ -271,6 +271,24 @@ static ChainTopo topo_of(const DsfMano* h) {
 //   PCA pose -> axis angles (mano_layer.py:601), Rodrigues (:720-728), pose feature (:611),
 //   rest joints from beta (:586-591), kinematic chain by tree level (:730-770).
 // ------------------------------------------------------------------------------------------------
+// stage the PCA basis (45 x 45) and the rest-joint regressor (10 x NJ x 3) in shared memory with cp.async: every
+// copy is in flight at once and no register waits for a load (a load -> store loop per thread serialises on the
+// global latency).  Both tables are cudaMalloc'ed (16-byte aligned); 4-byte copies, 128 threads: 20 per thread.
+__device__ __forceinline__ void stage_pose_tables(float* s_comp, float* s_JS, const float* comp, const float* JS, int tid,
+                                                  int nthr) {
+#ifdef POSE_STAGE_LDG
+    for (int i = tid; i < 45 * 45; i += nthr) s_comp[i] = __ldg(comp + i);
+    for (int i = tid; i < 10 * NJ * 3; i += nthr) s_JS[i] = __ldg(JS + i);
+#else
+    for (int i = tid; i < 45 * 45; i += nthr)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_comp + i)), "l"(comp + i) : "memory");
+    for (int i = tid; i < 10 * NJ * 3; i += nthr)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_JS + i)), "l"(JS + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 #define POSE_HPB 8   // hands per block (128 threads)
 
 __global__ void __launch_bounds__(POSE_HPB* NJ)
@@ -284,8 +302,7 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     // with coalesced loads instead of walking an 8 KB table through L1 one 180-byte row per iteration
     __shared__ float s_comp[45 * 45];
     __shared__ float s_JS[10 * NJ * 3];
-    for (int i = threadIdx.x; i < 45 * 45; i += POSE_HPB * NJ) s_comp[i] = __ldg(comp + i);
-    for (int i = threadIdx.x; i < 10 * NJ * 3; i += POSE_HPB * NJ) s_JS[i] = __ldg(JS + i);
+    stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);
     __syncthreads();
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
@@ -766,8 +783,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     __shared__ float s_gang[POSE_HPB][48];
     __shared__ float s_comp[45 * 45];           // staged once per block, see mano_pose_kernel
     __shared__ float s_JS[10 * NJ * 3];
-    for (int i = threadIdx.x; i < 45 * 45; i += POSE_HPB * NJ) s_comp[i] = __ldg(comp + i);
-    for (int i = threadIdx.x; i < 10 * NJ * 3; i += POSE_HPB * NJ) s_JS[i] = __ldg(JS + i);
+    stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);
     __syncthreads();
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
