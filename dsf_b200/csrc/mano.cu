@@ -783,21 +783,50 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     __shared__ float s_gang[POSE_HPB][48];
     __shared__ float s_comp[45 * 45];           // staged once per block, see mano_pose_kernel
     __shared__ float s_JS[10 * NJ * 3];
-    stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);
-    __syncthreads();
+    // every per-hand input of the block (the joints' forward records and the skinning cotangent g_A: 2.75 KB per
+    // hand) is staged with 16-byte cp.async copies issued together with the tables: nothing in the kernel then waits
+    // on a dependent global load (the tree walk used to fetch the parent's record from the workspace at every level)
+    __shared__ __align__(16) float s_rj[POSE_HPB][NJ * RJ_STRIDE];
+    __shared__ __align__(16) float s_ga[POSE_HPB][NJ * 12];
+    __shared__ float s_gx[POSE_HPB][KP + 4];    // split-K partials of g_X summed per hand
+    for (int i = threadIdx.x; i < POSE_HPB * (NJ * RJ_STRIDE / 4 + NJ * 12 / 4); i += POSE_HPB * NJ) {
+        const int h_ = i / (NJ * RJ_STRIDE / 4 + NJ * 12 / 4), q = i % (NJ * RJ_STRIDE / 4 + NJ * 12 / 4);
+        const int hs = min(blockIdx.x * POSE_HPB + h_, B - 1);
+        const float* row = ws + (size_t)hs * WS_PER_HAND;
+        const bool is_rj = q < NJ * RJ_STRIDE / 4;
+        const float* src = is_rj ? row + WS_RJ + 4 * q : row + WS_GA + 4 * (q - NJ * RJ_STRIDE / 4);
+        float* dst = is_rj ? &s_rj[h_][4 * q] : &s_ga[h_][4 * (q - NJ * RJ_STRIDE / 4)];
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    }
+    stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);     // commits and waits for all copies
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
     const int hand = blockIdx.x * POSE_HPB + hl;
     const bool live = hand < B;
     const int hh = live ? hand : B - 1;
     const float* wsh = ws + (size_t)hh * WS_PER_HAND;
-    const float* rj = wsh + WS_RJ + j * RJ_STRIDE;
+    {   // g_X = sum of the split-K partials, fixed order; the hand's 16 lanes walk the 148 columns together
+        float a[(KP + NJ - 1) / NJ];
+#pragma unroll
+        for (int t = 0; t < (KP + NJ - 1) / NJ; ++t) a[t] = 0.f;
+        for (int z = 0; z < n_split; ++z)
+#pragma unroll
+            for (int t = 0; t < (KP + NJ - 1) / NJ; ++t) {
+                const int c = j + t * NJ;
+                if (c < KP) a[t] += wsh[WS_GX + z * KP + c];
+            }
+#pragma unroll
+        for (int t = 0; t < (KP + NJ - 1) / NJ; ++t)
+            if (j + t * NJ < KP) s_gx[hl][j + t * NJ] = a[t];
+    }
+    __syncthreads();
+    const float* rj = &s_rj[hl][j * RJ_STRIDE];
     float R[9], Gr[9], J[3], ang[3];
 #pragma unroll
     for (int e = 0; e < 9; ++e) { R[e] = rj[RJ_R + e]; Gr[e] = rj[RJ_GR + e]; }
 #pragma unroll
     for (int e = 0; e < 3; ++e) { J[e] = rj[RJ_J + e]; ang[e] = rj[RJ_ANG + e]; }
-    const float* ga = wsh + WS_GA + j * 12;
+    const float* ga = &s_ga[hl][j * 12];
     float gAt[3] = {ga[9], ga[10], ga[11]};
     // A_r = Gr, A_t = Gt - Gr J
     float tmp[3];
@@ -816,7 +845,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     for (int lvl = topo.maxlevel; lvl >= 1; --lvl) {
         if (topo.level[j] == lvl) {
             const int pj = topo.parents[j];
-            const float* prj = wsh + WS_RJ + pj * RJ_STRIDE;
+            const float* prj = &s_rj[hl][pj * RJ_STRIDE];
             float Pg[9], Pj[3];
 #pragma unroll
             for (int e = 0; e < 9; ++e) Pg[e] = prj[RJ_GR + e];
@@ -865,15 +894,8 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     }
     // pose blend shapes: pose_feature = Rs - I
     if (j >= 1) {
-        const float* gx = wsh + WS_GX + 10 + 9 * (j - 1);
-        float a9[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) a9[e] = 0.f;
-        for (int z = 0; z < n_split; ++z)                              // fixed order: deterministic; nine independent
-#pragma unroll
-            for (int e = 0; e < 9; ++e) a9[e] += gx[z * KP + e];       // loads in flight per split
-#pragma unroll
-        for (int e = 0; e < 9; ++e) gR[e] += a9[e];
+        for (int e = 0; e < 9; ++e) gR[e] += s_gx[hl][10 + 9 * (j - 1) + e];
     }
     __syncwarp();
     if (j == 0 && p.quat_dim == 4) {
@@ -900,8 +922,7 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
             g.theta[(size_t)hh * g.ld_theta + k] = a;
         }
         if (j < 10) {                                  // direct blend-shape term + rest-joint term
-            float a = 0.f;
-            for (int z = 0; z < n_split; ++z) a += wsh[WS_GX + z * KP + j];
+            float a = s_gx[hl][j];
             for (int i = 0; i < NJ; ++i) {
                 const float* gj = &s_acc[hl][i][12];
                 const float* js = s_JS + (j * NJ + i) * 3;
