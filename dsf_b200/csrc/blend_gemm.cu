@@ -321,8 +321,15 @@ tf32x3_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
     float* stage0 = reinterpret_cast<float*>(gsm);
     __shared__ __align__(8) unsigned long long full[G_NST], empty[G_NST], done;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[BN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * BN;
+    // the tile's bias row goes to shared memory now, long before the epilogue wants it
+    if (tid < BN / 4) {
+        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && n0 + 4 * tid < N) bz = __ldg(reinterpret_cast<const float4*>(bias + n0) + tid);
+        reinterpret_cast<float4*>(s_bias)[tid] = bz;
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(TM_COLS));
@@ -374,36 +381,43 @@ tf32x3_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done))
                      : "memory");
     }
-    // ---- epilogue (all warps): accumulator complete -> TMEM -> registers -> (+ bias) -> global
+    // ---- epilogue (all warps): accumulator complete -> TMEM -> registers (+ bias) -> shared memory (the operand
+    // ring is idle now) -> global.  tcgen05.ld hands every lane one ROW of the tile; storing from there would put
+    // the 32 lanes of a store on 32 different rows (16 bytes each, 23 KB apart).  Through shared memory each warp
+    // writes whole 512-byte row segments instead.
     mbar_wait(smem_u32(&done), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const int row = m0 + warp * 32 + lane;
-    float* crow = C + (size_t)row * ldc;
+    constexpr int PITCH = BN + 4;                       // floats; keeps the 16-byte row-wise stores off one bank group
+    float* stile = stage0;
+    {
+        float* srow = stile + (warp * 32 + lane) * PITCH;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-                const int n = n0 + c0 + i;
-                if (n < N) {
-                    float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                           __uint_as_float(v[i + 3]));
-                    if (bias) {
-                        const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + n));
-                        o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
-                    }
-                    *reinterpret_cast<float4*>(crow + n) = o;
-                }
+                const float4 bz = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+                *reinterpret_cast<float4*>(srow + c0 + i) =
+                    make_float4(__uint_as_float(v[i]) + bz.x, __uint_as_float(v[i + 1]) + bz.y,
+                                __uint_as_float(v[i + 2]) + bz.z, __uint_as_float(v[i + 3]) + bz.w);
             }
         }
+    }
+    __syncwarp();                                       // a warp stores exactly the 32 rows it wrote
+    for (int r = 0; r < 32; ++r) {
+        const int row = m0 + warp * 32 + r;
+#pragma unroll
+        for (int c = 4 * lane; c < BN; c += 128)
+            if (row < M && n0 + c < N)                  // N and the column offsets are multiples of 4
+                *reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c) =
+                    *reinterpret_cast<const float4*>(stile + (warp * 32 + r) * PITCH + c);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
