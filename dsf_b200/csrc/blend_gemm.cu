@@ -226,38 +226,49 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, const float
         if (!PRESPLIT && n_steps > 1) mbar_wait(smem_u32(&mbar[(last - 1) & 1]), (uint32_t)(((last - 1) >> 1) & 1));
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const int row = m0 + warp * 32 + lane;
-    float* crow = C + (size_t)blockIdx.z * split_stride + (size_t)row * ldc;
+    // TMEM -> registers (+ bias) -> shared memory (the operand stages are idle now) -> global: tcgen05.ld hands each
+    // lane one ROW of the tile, so a direct store would scatter every instruction over 32 rows; through shared
+    // memory each warp writes contiguous row segments.
+    constexpr int PITCH = BN + 4;
+    float* stile = stage0;
+    {
+        float* srow = stile + (warp * 32 + lane) * PITCH;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        if (n_steps > 0) {
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            if (n_steps > 0) {
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
-        }
-        if (row < M) {
+                for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
+                float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                       __uint_as_float(v[i + 3]));
                 const int n = n0 + c0 + i;
-                if (n < N) {          // N and the column offsets are multiples of 4
-                    float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                           __uint_as_float(v[i + 3]));
-                    if (bias) {
-                        const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + n));
-                        o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
-                    }
-                    *reinterpret_cast<float4*>(crow + n) = o;
+                if (bias && n < N) {          // N and the column offsets are multiples of 4
+                    const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + n));
+                    o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
                 }
+                *reinterpret_cast<float4*>(srow + c0 + i) = o;
             }
         }
+    }
+    __syncwarp();                                       // a warp stores exactly the 32 rows it wrote
+    for (int r = 0; r < 32; ++r) {
+        const int row = m0 + warp * 32 + r;
+        float* crow = C + (size_t)blockIdx.z * split_stride + (size_t)row * ldc;
+#pragma unroll
+        for (int c = 4 * lane; c < BN; c += 128)
+            if (row < M && n0 + c < N)
+                *reinterpret_cast<float4*>(crow + n0 + c) = *reinterpret_cast<const float4*>(stile + (warp * 32 + r) * PITCH + c);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
