@@ -323,7 +323,12 @@ template <int BN>
 __global__ void __launch_bounds__(G_THREADS)
 tf32x3_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int M, int N,
-                       int n_kb, float* __restrict__ C, int ldc, const float* __restrict__ bias) {
+                       int n_kb_total, int kb_per_split, float* __restrict__ C, int ldc, long split_stride,
+                       const float* __restrict__ bias) {
+    // split-K: grid.z slices of kb_per_split k blocks, partial products to C + z * split_stride (the consumer sums)
+    const int kb_lo = blockIdx.z * kb_per_split;
+    const int n_kb = max(0, min(n_kb_total, kb_lo + kb_per_split) - kb_lo);
+    C += (size_t)blockIdx.z * split_stride;
     constexpr int TM_COLS = BN <= 128 ? 128 : 256;
     constexpr int A_FLOATS = GM * GKB, B_FLOATS = BN * GKB;
     constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
@@ -368,10 +373,10 @@ tf32x3_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
             const uint32_t bar = smem_u32(&full[s]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STAGE_BYTES) : "memory");
             float* sAh = stage0 + s * STAGE_FLOATS;
-            tma_load_2d(smem_u32(sAh), &tmAh, kb * GKB, m0, bar);
-            tma_load_2d(smem_u32(sAh + A_FLOATS), &tmAl, kb * GKB, m0, bar);
-            tma_load_2d(smem_u32(sAh + 2 * A_FLOATS), &tmBh, kb * GKB, n0, bar);
-            tma_load_2d(smem_u32(sAh + 2 * A_FLOATS + B_FLOATS), &tmBl, kb * GKB, n0, bar);
+            tma_load_2d(smem_u32(sAh), &tmAh, (kb_lo + kb) * GKB, m0, bar);
+            tma_load_2d(smem_u32(sAh + A_FLOATS), &tmAl, (kb_lo + kb) * GKB, m0, bar);
+            tma_load_2d(smem_u32(sAh + 2 * A_FLOATS), &tmBh, (kb_lo + kb) * GKB, n0, bar);
+            tma_load_2d(smem_u32(sAh + 2 * A_FLOATS + B_FLOATS), &tmBl, (kb_lo + kb) * GKB, n0, bar);
         }
     } else if (tid == 32) {
         // ---- MMA issuer
@@ -412,6 +417,10 @@ tf32x3_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n_kb == 0) {                           // a split-K slice beyond the last k block contributes zeros
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 bz = *reinterpret_cast<const float4*>(s_bias + c0 + i);
@@ -513,7 +522,8 @@ int dsf_blend_forward_gemm(int M, const float* Ah, const float* Al, int lda, con
             if (dev < 16) attr_set[dev] = true;
         }
         dim3 grid((NP + 127) / 128, (M + GM - 1) / GM);
-        tf32x3_gemm_tma_kernel<128><<<grid, G_THREADS, smem, st>>>(tAh, tAl, tBh, tBl, M, NP, BLEND_KPAD / GKB, C, ldc, bias);
+        tf32x3_gemm_tma_kernel<128><<<grid, G_THREADS, smem, st>>>(tAh, tAl, tBh, tBl, M, NP, BLEND_KPAD / GKB, BLEND_KPAD / GKB, C, ldc,
+                                                                   0, bias);
         DSF_CHECK_LAUNCH();
         return DSF_OK;
     }
@@ -530,8 +540,33 @@ int dsf_blend_backward_splits(int M) {
     return s < 4 ? 4 : (s > BLEND_SPLITS ? BLEND_SPLITS : s);
 }
 
-int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
-                            long split_stride, cudaStream_t st) {
-    return launch_tf32x3<160, false>(M, KP, NP, A, nullptr, lda, Bh, Bl, NP, C, ldc, split_stride, nullptr,
-                                     dsf_blend_backward_splits(M), st);
+int dsf_blend_backward_gemm(int M, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, float* C,
+                            int ldc, long split_stride, cudaStream_t st) {
+    // The cotangent arrives pre-split (mano_skin_bwd_kernel), so the backward contraction runs through the same
+    // TMA-fed, warp-specialised pipeline as the forward one: 128 x 160 tiles, split-K over grid.z.
+    const int n_split = dsf_blend_backward_splits(M);
+    static int tma_state = 0;
+    CUtensorMap tAh, tAl, tBh, tBl;
+    if (tma_state >= 0 && dsf_make_operand_tmap(&tAh, Ah, M, NP, lda, GM) && dsf_make_operand_tmap(&tAl, Al, M, NP, lda, GM) &&
+        dsf_make_operand_tmap(&tBh, Bh, BLEND_KPAD, NP, NP, 160) && dsf_make_operand_tmap(&tBl, Bl, BLEND_KPAD, NP, NP, 160)) {
+        tma_state = 1;
+        const size_t smem = (size_t)G_NST * 2 * (GM + 160) * GKB * sizeof(float);
+        static bool attr_set[16] = {};
+        int dev = 0;
+        DSF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 16 || !attr_set[dev]) {
+            DSF_CHECK_CUDA(cudaFuncSetAttribute(tf32x3_gemm_tma_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            if (dev < 16) attr_set[dev] = true;
+        }
+        const int nkb = NP / GKB;
+        const int kbs = (nkb + n_split - 1) / n_split;
+        dim3 grid(1, (M + GM - 1) / GM, n_split);
+        tf32x3_gemm_tma_kernel<160><<<grid, G_THREADS, smem, st>>>(tAh, tAl, tBh, tBl, M, KP, nkb, kbs, C, ldc, split_stride,
+                                                                   nullptr);
+        DSF_CHECK_LAUNCH();
+        return DSF_OK;
+    }
+    tma_state = -1;
+    return launch_tf32x3<160, true>(M, KP, NP, Ah, Al, lda, Bh, Bl, NP, C, ldc, split_stride, nullptr, n_split, st);
 }

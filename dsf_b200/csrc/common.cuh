@@ -30,8 +30,9 @@
 #define WS_X 0                            // GEMM operand [beta | Rs - I | 0], split into tf32 hi (BLEND_KPAD) and lo (BLEND_KPAD)
 #define WS_VP (WS_X + 2 * BLEND_KPAD)
 #define WS_RJ (WS_VP + NP)
-#define WS_GVP (WS_RJ + NJ * RJ_STRIDE)
-#define WS_GA (WS_GVP + NP)
+#define WS_GVP (WS_RJ + NJ * RJ_STRIDE)   // skinning cotangent g_vposed, tf32 hi part ...
+#define WS_GVPL (WS_GVP + NP)             // ... and lo part (operand of the backward blend GEMM, written pre-split)
+#define WS_GA (WS_GVPL + NP)
 #define WS_GX (WS_GA + NJ * 12)          // BLEND_SPLITS split-K partials of g_X, KP floats each
 #define WS_PER_HAND (WS_GX + BLEND_SPLITS * KP)
 // the MANO scratch holds whole groups of 8 hands (the tensor maps of the blend GEMM address rows in groups of 8)

@@ -410,8 +410,8 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
 // K2: the blend-shape contraction runs on the tensor cores, see blend_gemm.cu
 int dsf_blend_forward_gemm(int M, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, float* C,
                            int ldc, const float* bias, cudaStream_t st);
-int dsf_blend_backward_gemm(int M, const float* A, int lda, const float* Bh, const float* Bl, float* C, int ldc,
-                            long split_stride, cudaStream_t st);
+int dsf_blend_backward_gemm(int M, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, float* C,
+                            int ldc, long split_stride, cudaStream_t st);
 int dsf_blend_backward_splits(int M);
 
 // ------------------------------------------------------------------------------------------------
@@ -723,11 +723,18 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
 #pragma unroll
             for (int e = 0; e < 9; ++e) T[e] = fmaf(wgt, sGr[en.x][e], T[e]);
         }
-        GVP[3 * v] = T[0] * g0 + T[3] * g1 + T[6] * g2;
-        GVP[3 * v + 1] = T[1] * g0 + T[4] * g1 + T[7] * g2;
-        GVP[3 * v + 2] = T[2] * g0 + T[5] * g1 + T[8] * g2;
+        // written already split for the 3xTF32 tensor-core GEMM (hi = low 13 mantissa bits cleared, lo = the rest):
+        // the backward contraction then streams both operands asynchronously instead of splitting in registers
+        const float o[3] = {T[0] * g0 + T[3] * g1 + T[6] * g2, T[1] * g0 + T[4] * g1 + T[7] * g2,
+                            T[2] * g0 + T[5] * g1 + T[8] * g2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float hi = __uint_as_float(__float_as_uint(o[c]) & 0xFFFFE000u);
+            GVP[3 * v + c] = hi;
+            GVP[NP + 3 * v + c] = o[c] - hi;
+        }
     }
-    if (tid < NP - NV * 3) GVP[NV * 3 + tid] = 0.f;
+    if (tid < NP - NV * 3) { GVP[NV * 3 + tid] = 0.f; GVP[NP + NV * 3 + tid] = 0.f; }
     __syncthreads();
     // g_A[j] = sum_v w_vj [ g (x) vp | g ] over the vertices joint j actually moves: one warp per
     // joint walks that joint's weight list (CSR) and reduces with shuffles
@@ -1000,7 +1007,7 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
                                               lf ? *lf : LossFold{});
     DSF_CHECK_LAUNCH();
     // g_X = g_vposed . basis^T as BLEND_SPLITS split-K partials (summed by the pose backward kernel)
-    rc = dsf_blend_backward_gemm(B, ws + WS_GVP, WS_PER_HAND, h->Bh, h->Bl, ws + WS_GX, WS_PER_HAND, KP, st);
+    rc = dsf_blend_backward_gemm(B, ws + WS_GVP, ws + WS_GVPL, WS_PER_HAND, h->Bh, h->Bl, ws + WS_GX, WS_PER_HAND, KP, st);
     if (rc) return rc;
     mano_pose_bwd_kernel<<<(B + POSE_HPB - 1) / POSE_HPB, POSE_HPB * NJ, 0, st>>>(B, *p, *g, h->comp, h->JS,
                                                                                   topo, ws, dsf_blend_backward_splits(B),
