@@ -7,11 +7,14 @@
 // Vertices must match the fp32 reference to 1e-5, which single-pass TF32 (10-bit mantissa) cannot
 // give, so every product is computed error-compensated ("3xTF32"):
 //       a.b  ~=  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi,     a_hi = a with the low 13 mantissa bits cleared
-// The basis is split into hi/lo once on the host (cp.async straight into shared memory); the
-// activation tile is read once per k block and split on the fly into a hi and a lo operand tile.  One CTA = one 128-row tile: tcgen05.mma (kind::tf32, M=128,
-// N=128 or 160, K=8) issued by a single thread, fp32 accumulator in TMEM, operands in shared memory
-// in the canonical no-swizzle K-major core-matrix layout, two smem stages guarded by mbarriers that
-// tcgen05.commit arrives on, epilogue tcgen05.ld -> registers -> global.
+// The basis is split into hi/lo once on the host; the activations arrive pre-split from their producers (the pose
+// kernel writes [beta | Rs - I], the skinning backward writes g_vposed, both as hi and lo rows of the workspace).
+// Both directions run through ONE kernel, tf32x3_gemm_tma_kernel: a 128-row tile per CTA, tcgen05.mma (kind::tf32,
+// M = 128, N = 128 forward / 160 backward, K = 8) issued by a single thread, fp32 accumulator in TMEM, operand tiles
+// streamed by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a three-stage ring guarded by full / empty
+// mbarriers, split-K over grid.z for the backward contraction, epilogue TMEM -> registers (+ bias) -> shared memory
+// -> coalesced row segments.  tf32x3_gemm_kernel is the cp.async fallback for drivers without the tensor-map entry
+// point (canonical no-swizzle K-major core-matrix layout).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -63,16 +66,16 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem, uint32_t a_base, uint32
     }
 }
 
-// PRESPLIT: the activation arrives already split (A = hi part, Alo = lo part, both zero padded to a multiple of GKB
-// columns): every operand then travels by cp.async and the k blocks run through a three-stage ring, so the loads of
-// blocks s + 1, s + 2 are in flight while block s is multiplied.  Otherwise (backward: the activation is the
-// skinning cotangent in plain fp32) two stages with the split done in registers on the way into shared memory.
+// cp.async fallback (no tensor maps): the activation arrives already split (A = hi part, Alo = lo part, both zero
+// padded to a multiple of GKB columns); every operand travels by 16-byte cp.async copies into the no-swizzle
+// core-matrix layout and the k blocks run through a three-stage ring, so the loads of blocks s + 1, s + 2 are in
+// flight while block s is multiplied.
 template <int BN, bool PRESPLIT>
 __global__ void __launch_bounds__(G_THREADS)
 tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ Alo, int lda,
                    const float* __restrict__ Bh, const float* __restrict__ Bl, int ldb, float* __restrict__ C, int ldc,
                    long split_stride, const float* __restrict__ bias, int kb_per_split) {
-    constexpr int NST = PRESPLIT ? 3 : 2;
+    constexpr int NST = 3;
     constexpr int TM_COLS = BN <= 128 ? 128 : 256;
     constexpr int A_FLOATS = GM * GKB, B_FLOATS = BN * GKB;
     constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;       // A_hi, A_lo, B_hi, B_lo
@@ -105,7 +108,8 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, const float
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
 
-    if (PRESPLIT) {
+    {
+        static_assert(PRESPLIT, "the activation always arrives pre-split now");
         // every operand by cp.async (rows beyond M re-read row M - 1: their accumulator rows are never stored)
         auto issue_loads = [&](int step) {
             const int k0 = (kb_lo + step) * GKB;
@@ -157,73 +161,11 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, const float
                 issue_loads(step + NST);
             }
         }
-    } else {
-    // thread -> (8-row group, 16-byte k chunk): conflict-free 16-byte shared stores
-    auto load_a = [&](int k0, float4* av) {
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) {
-            const int q = i * G_THREADS + tid;
-            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < M && k0 + k < K) av[i] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + k);
-        }
-    };
-    float4 av[A_IT];
-    if (n_steps > 0) load_a(kb_lo * GKB, av);
-
-    for (int step = 0; step < n_steps; ++step) {
-        const int s = step & 1;
-        const int k0 = (kb_lo + step) * GKB;
-        float* sAh = stage0 + s * STAGE_FLOATS;
-        float* sAl = sAh + A_FLOATS;
-        float* sBh = sAl + A_FLOATS;
-        float* sBl = sBh + B_FLOATS;
-        if (step >= 2) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((step >> 1) - 1) & 1));
-        // basis tiles (already split on the host, zero padded): asynchronous 16-byte copies
-#pragma unroll
-        for (int i = 0; i < B_IT; ++i) {
-            const int q = i * G_THREADS + tid;
-            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            const size_t go = (size_t)(n0 + r) * ldb + k0 + k;
-            cp_async16(sBh + tile_idx(r, k), Bh + go);
-            cp_async16(sBl + tile_idx(r, k), Bl + go);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // activation tile: split into tf32 hi / lo on the way into shared memory
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) {
-            const int q = i * G_THREADS + tid;
-            const int r = (q >> 6) * 8 + (q & 7), k = ((q & 63) >> 3) * 4;
-            const float4 v = av[i];
-            float4 h;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(sAh + tile_idx(r, k)) = h;
-            *reinterpret_cast<float4*>(sAl + tile_idx(r, k)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        }
-        if (step + 1 < n_steps) load_a(k0 + GKB, av);          // prefetch the next activation tile
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t ah = smem_u32(sAh), al = smem_u32(sAl), bh = smem_u32(sBh), bl = smem_u32(sBl);
-            issue_mma(tmem, ah, bh, idesc, step == 0);      // a_hi . b_hi
-            issue_mma(tmem, ah, bl, idesc, false);          // a_hi . b_lo
-            issue_mma(tmem, al, bh, idesc, false);          // a_lo . b_hi
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             smem_u32(&mbar[s]))
-                         : "memory");
-        }
-    }
     }
     // ---- epilogue: wait for the last commit (covers every earlier MMA), TMEM -> registers -> global
     if (n_steps > 0) {
         const int last = n_steps - 1;
         mbar_wait(smem_u32(&mbar[last % NST]), (uint32_t)((last / NST) & 1));
-        if (!PRESPLIT && n_steps > 1) mbar_wait(smem_u32(&mbar[(last - 1) & 1]), (uint32_t)(((last - 1) >> 1) & 1));
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
     // TMEM -> registers (+ bias) -> shared memory (the operand stages are idle now) -> global: tcgen05.ld hands each
@@ -481,7 +423,7 @@ bool dsf_make_operand_tmap(CUtensorMap* tm, const float* base, long rows, int K,
 template <int BN, bool PRESPLIT>
 static int launch_tf32x3(int M, int N, int K, const float* A, const float* Alo, int lda, const float* Bh, const float* Bl,
                          int ldb, float* C, int ldc, long split_stride, const float* bias, int n_split, cudaStream_t st) {
-    const size_t smem = (size_t)(PRESPLIT ? 3 : 2) * 2 * (GM + BN) * GKB * sizeof(float);
+    const size_t smem = (size_t)3 * 2 * (GM + BN) * GKB * sizeof(float);
     static bool attr_set[16] = {};
     int dev = 0;
     DSF_CHECK_CUDA(cudaGetDevice(&dev));
