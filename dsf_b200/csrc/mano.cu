@@ -614,22 +614,52 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
     // the loss record) are worked out once, by thread 0, not by every thread.
     __shared__ float s_gts;
     __shared__ int s_live[9];                 // [0] = number of live tiles (-1: more than 8 tiles, general path), then ids
-    if (tid == 0) {
-        s_gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
-        int n_live = -1;
-        if (gt.gv_tile && gt.n_tiles <= 8) {
-            n_live = 0;
-            for (int t = 0; t < gt.n_tiles; ++t)
-                if (gt.gv_flag[(size_t)hand * gt.n_tiles + t]) s_live[1 + n_live++] = t;
-        }
-        s_live[0] = n_live;
-        if (lf.parts && lf.n_mesh == B) {                   // per-hand loss record = sum of its tiles
+    if (warp == 0) {
+        // lane t fetches tile t's records, all at once (a scalar loop would pay one global round trip per record);
+        // the sums then run over the lanes in ascending tile order, as grad_tiles_scale / the fold kernels do
+        const bool has_t = (gt.gv_tile != nullptr || lf.parts != nullptr);
+        const int nt = gt.gv_tile ? gt.n_tiles : lf.n_tiles;
+        const float* pt_base = gt.gv_tile ? gt.parts_tile : lf.parts_tile;
+        float my_sum = 0.f, my_cnt = 0.f;
+        int my_flag = 0;
+        for (int t0 = 0; t0 < (has_t ? nt : 0); t0 += 32) {          // one trip unless there are more than 32 tiles
+            const int t = t0 + lane;
             float a = 0.f, c = 0.f;
-            for (int t = 0; t < lf.n_tiles; ++t) {
-                a += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2];
-                c += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2 + 1];
+            int f = 0;
+            if (t < nt) {
+                a = pt_base[((size_t)hand * nt + t) * 2];
+                c = pt_base[((size_t)hand * nt + t) * 2 + 1];
+                if (gt.gv_tile) f = gt.gv_flag[(size_t)hand * nt + t];
             }
-            lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
+            if (t0 == 0) { my_sum = a; my_cnt = c; my_flag = f; }
+        }
+        const float zh = (gt.gv_tile && lane == 0) ? cube[3 * hand + 2] * 0.5f : 0.f;
+        if (nt <= 32 && has_t) {
+            float a = 0.f, c = 0.f;
+            int n_live = 0;
+            for (int t = 0; t < nt; ++t) {
+                a += __shfl_sync(0xffffffffu, my_sum, t);
+                c += __shfl_sync(0xffffffffu, my_cnt, t);
+                const int f = __shfl_sync(0xffffffffu, my_flag, t);
+                if (lane == 0 && f && nt <= 8) s_live[1 + n_live] = t;
+                n_live += f ? 1 : 0;
+            }
+            if (lane == 0) {
+                s_gts = gt.gv_tile ? gt.gscale / (c + 1e-8f) / zh : 0.f;
+                s_live[0] = (gt.gv_tile && nt <= 8) ? n_live : -1;
+                if (lf.parts && lf.n_mesh == B) { lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c; }
+            }
+        } else if (lane == 0) {                                       // general path
+            s_gts = gt.gv_tile ? grad_tiles_scale(gt, hand, cube[3 * hand + 2] * 0.5f) : 0.f;
+            s_live[0] = -1;
+            if (lf.parts && lf.n_mesh == B) {
+                float a = 0.f, c = 0.f;
+                for (int t = 0; t < lf.n_tiles; ++t) {
+                    a += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2];
+                    c += lf.parts_tile[((size_t)hand * lf.n_tiles + t) * 2 + 1];
+                }
+                lf.parts[2 * hand] = a; lf.parts[2 * hand + 1] = c;
+            }
         }
     }
     __syncthreads();                          // also: the mbarrier is initialised before anyone polls it
@@ -642,8 +672,10 @@ mano_skin_bwd_kernel(int B, float* __restrict__ ws, const int* __restrict__ wv_p
         asm volatile(
             "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n" ::"r"(bar)
             : "memory");
-        if (n_live_tiles >= 1) tile0 = reinterpret_cast<const float*>(s_tiles[s_live[1]] + t_shift[s_live[1]]);
-        if (n_live_tiles >= 2) tile1 = reinterpret_cast<const float*>(s_tiles[s_live[2]] + t_shift[s_live[2]]);
+        // (select, not index: keeps t_shift in registers)
+        if (n_live_tiles >= 1) tile0 = s_live[1] == 0 ? reinterpret_cast<const float*>(s_tiles[0] + t_shift[0])
+                                                      : reinterpret_cast<const float*>(s_tiles[1] + t_shift[1]);
+        if (n_live_tiles >= 2) tile1 = reinterpret_cast<const float*>(s_tiles[1] + t_shift[1]);
     } else {
         if (n_live_tiles >= 1) tile0 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[1]) * NVW * 3;
         if (n_live_tiles >= 2) tile1 = gt.gv_tile + ((size_t)hand * gt.n_tiles + s_live[2]) * NVW * 3;
