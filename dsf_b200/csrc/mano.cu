@@ -346,11 +346,16 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
         J[1] = fmaf(be, s_JS[(b * NJ + j) * 3 + 1], J[1]);
         J[2] = fmaf(be, s_JS[(b * NJ + j) * 3 + 2], J[2]);
     }
-    float* wsh = ws + (size_t)hh * WS_PER_HAND;
-    if (live) {
-        // GEMM operand row X = [beta | Rs - I | 0], written already split for the 3xTF32 tensor-core GEMM:
+    // The kernel's outputs - the GEMM operand row and the 16 joint records of every hand - are collected in shared
+    // memory and leave as whole rows (16-byte stores, consecutive lanes on consecutive addresses) at the end: written
+    // from here, every store instruction would touch 32 different 128-byte lines (lane = joint, records 128 bytes
+    // apart), seven times the memory transactions the data needs.
+    __shared__ __align__(16) float s_X[POSE_HPB][2 * BLEND_KPAD];
+    __shared__ __align__(16) float s_out[POSE_HPB][NJ * RJ_STRIDE];
+    {
+        // GEMM operand row X = [beta | Rs - I | 0], already split for the 3xTF32 tensor-core GEMM:
         // hi = the value with the low 13 mantissa bits cleared (exact in tf32), lo = the remainder
-        float* Xh = wsh + WS_X;
+        float* Xh = s_X[hl];
         float* Xl = Xh + BLEND_KPAD;
         auto put = [&](int k, float v) {
             const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -391,8 +396,8 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
         }
         __syncwarp();
     }
-    if (live) {
-        float* o = wsh + WS_RJ + j * RJ_STRIDE;
+    {
+        float* o = &s_out[hl][j * RJ_STRIDE];
         float GJ[3];
         mat3_vec(Gr, J, GJ);
 #pragma unroll
@@ -404,6 +409,18 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
             o[RJ_AT + e] = Gt[e] - GJ[e];   // A = G - [0 | G.J]  (mano_layer.py:765-768)
             o[RJ_ANG + e] = ang[e];
         }
+        o[30] = 0.f; o[31] = 0.f;           // pad of the record
+    }
+    __syncthreads();
+    // rows out: per hand 2 * BLEND_KPAD / 4 + NJ * RJ_STRIDE / 4 = 208 float4 (workspace rows are 16-byte aligned)
+    constexpr int XQ = 2 * BLEND_KPAD / 4, RQ = NJ * RJ_STRIDE / 4;
+    for (int i = threadIdx.x; i < POSE_HPB * (XQ + RQ); i += POSE_HPB * NJ) {
+        const int h_ = i / (XQ + RQ), q = i % (XQ + RQ);
+        const int hd = blockIdx.x * POSE_HPB + h_;
+        if (hd >= B) continue;
+        float* row = ws + (size_t)hd * WS_PER_HAND;
+        if (q < XQ) reinterpret_cast<float4*>(row + WS_X)[q] = reinterpret_cast<const float4*>(s_X[h_])[q];
+        else reinterpret_cast<float4*>(row + WS_RJ)[q - XQ] = reinterpret_cast<const float4*>(s_out[h_])[q - XQ];
     }
 }
 
@@ -1009,6 +1026,7 @@ static int check_params(const DsfManoParams* p) {
 
 int dsf_mano_forward_impl(const DsfMano* h, int B, const DsfManoParams* p, float unit_scale, float* verts,
                           float* joints, float* Rs, float* ws, cudaStream_t st) {
+    DSF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
     int rc = ensure_constants();
     if (rc) return rc;
     ChainTopo topo = topo_of(h);
@@ -1029,6 +1047,7 @@ int dsf_mano_backward_impl(const DsfMano* h, int B, const DsfManoParams* p, floa
                            const float* verts, const float* joints, const float* g_verts,
                            const float* g_joints, const DsfManoGrads* g, float* ws, const GradTiles* gt,
                            const float* cube, const LossFold* lf, cudaStream_t st) {
+    DSF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
     int rc = ensure_constants();
     if (rc) return rc;
     ChainTopo topo = topo_of(h);
