@@ -23,6 +23,20 @@ sub = {
     "PCL": "%.3f" % o["img2pcl_batch1024"]["ms"], "I1": "%.1f" % o["I1_intersection_volume_batch256"]["ms"],
     "MFWD": "%.3f" % r["stage_ms"]["mano_forward(3 kernels)"], "MBWD": "%.3f" % r["stage_ms"]["mano_backward(3 kernels)"],
 }
+def line(path):
+    return json.loads([l for l in open(os.path.join(ROOT, path)) if l.startswith("{")][0])
+# the multi-GPU lines may come from an earlier build of the round than the N = 1 line: each names its own N = 1 base
+BASE = {"n2": 3.567e6, "n8": 3.567e6}
+try:
+    BASE.update(json.load(open(os.path.join(ROOT, "profiles/raw/r02_scale_bases.json"))))
+except FileNotFoundError:
+    pass
+n2, n8 = line("profiles/raw/r02_bench_n2.json"), line("profiles/raw/r02_bench_n8_strong.json")
+sub.update({"N2MS": "%.3f" % n2["ms_per_step"], "N2V": M(n2["value"]), "N2EFF": "%.2f" % (n2["value"] / (2 * BASE["n2"])),
+            "N2BASE": M(BASE["n2"]), "N8MS": "%.3f" % n8["ms_per_step"], "N8V": M(n8["value"]),
+            "N8EFF": "%.2f" % (n8["value"] / (8 * BASE["n8"])), "N8BASE": M(BASE["n8"]),
+            "N8WMS": "%.3f" % n8["weak_scaling"]["ms_per_step"], "N8WV": M(n8["weak_scaling"]["value"]),
+            "N8E2E": M(n8["e2e"]["value"])})
 rows = [x for x in csv.reader(open(os.path.join(ROOT, "profiles/raw/r02_launches_B4096.csv"))) if len(x) > 5]
 h = rows[0]
 t = collections.OrderedDict()
