@@ -32,6 +32,10 @@ try:
 except FileNotFoundError:
     pass
 n2, n8 = line("profiles/raw/r02_bench_n2.json"), line("profiles/raw/r02_bench_n8_strong.json")
+n4 = line("profiles/raw/r02_bench_n4_strong.json")
+BASE.setdefault("n4", BASE["n8"])
+sub.update({"N4MS": "%.3f" % n4["ms_per_step"], "N4V": M(n4["value"]), "N4EFF": "%.2f" % (n4["value"] / (4 * BASE["n4"])),
+            "N4E2E": M(n4["e2e"]["value"]), "N2E2E": M(n2["e2e"]["value"])})
 sub.update({"N2MS": "%.3f" % n2["ms_per_step"], "N2V": M(n2["value"]), "N2EFF": "%.2f" % (n2["value"] / (2 * BASE["n2"])),
             "N2BASE": M(BASE["n2"]), "N8MS": "%.3f" % n8["ms_per_step"], "N8V": M(n8["value"]),
             "N8EFF": "%.2f" % (n8["value"] / (8 * BASE["n8"])), "N8BASE": M(BASE["n8"]),
