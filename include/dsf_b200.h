@@ -72,7 +72,8 @@ typedef struct DsfManoHost {
 typedef struct DsfMano DsfMano;
 int dsf_mano_create(const DsfManoHost* host, DsfMano** out);
 int dsf_mano_free(DsfMano* h);
-/* floats of caller-provided scratch per call of dsf_mano_forward (kept for dsf_mano_backward) */
+/* floats of caller-provided scratch per call of dsf_mano_forward (kept for dsf_mano_backward); the scratch (and the
+ * workspace of the fused steps, which starts with it) must be 16-byte aligned: its rows travel by TMA / cp.async */
 long dsf_mano_workspace_floats(int batch);
 
 /* A (B, ...) parameter block addressed with row strides so the slices of a (B,62) tensor
