@@ -197,3 +197,61 @@ def test_point_face_sphere_bound_never_exceeds_reported_distance():
     # and the bound is useful: it exceeds a tenth of the distance for most far points
     far = ok[:, None] & (dist_c > 4 * rr[:, None])
     assert (lb[far] > 0.1 * d[far]).float().mean() > 0.9
+
+
+def test_point_face_box_bound_never_exceeds_reported_distance():
+    """The box hierarchy of the whole-mesh point-face kernel (point_face_fwd_all_kernel) skips a group of faces when
+    the squared distance from the point to the group's axis-aligned box exceeds `best` (0.02 % slack).  The box of a
+    face is the box of its triangle SCALED about v0 by k = 1.01 (den + eps) / den - the same region the bounding
+    sphere covers - grown by 1e-6 of the largest coordinate; a group's box is the union.  Restated here in float32
+    torch and checked against the oracle's reported distance on random, small and ill-conditioned triangles, alone
+    and in groups of 8: the bound must never exceed the distance to any member."""
+    from oracle import raster_oracle as ro
+
+    gen = torch.Generator().manual_seed(5)
+    T, P = 4000, 64
+    scale = 10 ** (torch.rand(T, 1, 1, generator=gen) * 3 - 3)
+    tri = torch.randn(T, 3, 3, generator=gen) * scale
+    tri[::7, 2] = tri[::7, 0] + (tri[::7, 1] - tri[::7, 0]) * 0.4 + 1e-6 * torch.randn(len(tri[::7]), 3, generator=gen)
+    tri = tri + torch.randn(T, 1, 3, generator=gen)
+    pts = tri.mean(1, keepdim=True) + torch.randn(T, P, 3, generator=gen) * scale * 10 ** (torch.rand(T, P, 1, generator=gen) * 3 - 2)
+    faces = torch.tensor([[0, 1, 2]], dtype=torch.int32)
+    d, _ = ro.point_face(pts.contiguous(), tri.contiguous(), faces)          # (T, P) squared distances
+    v0, e1, e2 = tri[:, 0], tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    d00, d01, d11 = (e1 * e1).sum(-1), (e1 * e2).sum(-1), (e2 * e2).sum(-1)
+    den = d00 * d11 - d01 * d01
+    k = torch.where((den > 1e-4 * d00 * d11) & (den > 1e-30), 1.01 * (den + 1e-8) / den, torch.full_like(den, float("inf")))
+    ok = k < 1e6                                                               # the kernel's never-cull flag otherwise
+    kk = torch.where(ok, k, torch.ones_like(k))
+    s1, s2 = e1 * kk[:, None], e2 * kk[:, None]
+    zero = torch.zeros_like(s1)
+    lo = v0 + torch.minimum(zero, torch.minimum(s1, s2))
+    hi = v0 + torch.maximum(zero, torch.maximum(s1, s2))
+    inf = torch.full_like(lo, float("inf"))
+    lo, hi = torch.where(ok[:, None], lo, -inf), torch.where(ok[:, None], hi, inf)
+
+    def grow(lo, hi):
+        m = 1e-6 * torch.maximum(lo.abs(), hi.abs()) + 1e-12
+        return lo - m, hi + m
+
+    def box_d2(p, lo, hi):                                                     # p (T,P,3), boxes (T,3)
+        dd = torch.maximum(torch.maximum(lo[:, None] - p, p - hi[:, None]), torch.zeros_like(p))
+        return (dd * dd).sum(-1)
+
+    glo, ghi = grow(lo, hi)
+    lb = box_d2(pts, glo, ghi)
+    viol = lb > d * 1.0002 + 1e-30
+    assert viol.sum() == 0, (int(viol.sum()), float((lb / d)[viol].max()))
+    assert ok.float().mean() > 0.6 and (~ok).sum() > 10
+    far = ok[:, None] & (lb > 0)
+    assert (lb[far] > 0.1 * d[far]).float().mean() > 0.5                       # and it is a useful bound
+    # groups of 8 consecutive faces: the union box bounds the distance of the group's points to EVERY member
+    G = T // 8
+    ulo, uhi = grow(lo[: G * 8].view(G, 8, 3).min(1)[0], hi[: G * 8].view(G, 8, 3).max(1)[0])
+    pg = pts[: G * 8: 8]                                                       # the first member's points
+    tri_g = tri[: G * 8].view(G, 8, 3, 3)
+    lbg = box_d2(pg, ulo, uhi)
+    for m in range(8):
+        dm, _ = ro.point_face(pg.contiguous(), tri_g[:, m].contiguous(), faces)
+        viol = lbg > dm * 1.0002 + 1e-30
+        assert viol.sum() == 0, (m, int(viol.sum()))
