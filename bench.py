@@ -284,7 +284,9 @@ def run_ours(args):
     inp_all = sample_fit_inputs(G, seed=1000)       # every rank draws the same batch and keeps its shard
     inp = {k: v[lo:hi] for k, v in inp_all.items()}
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in inp.items()}
-    n_chunks = lambda b: args.chunks if args.chunks > 0 else (2 if b >= 2048 else 1)
+    # stream slices per step, measured (tools/time_steps.py): 4096 hands 1.124 / 1.084 / 1.091 ms at 1 / 2 / 4 slices,
+    # 2048: 0.597 / 0.573 / 0.570, 1024: 0.339 / 0.326 / 0.321, 512: 0.200 / 0.207 (one slice is best below 1024)
+    n_chunks = lambda b: args.chunks if args.chunks > 0 else (2 if b >= 4096 else (4 if b >= 1024 else 1))
     mk = lambda b: FitStep(layer, b, CROP, use_graph=not args.no_graph, chunks=n_chunks(b), keep_pix_to_face=False)
     step = mk(B)
     step.set_inputs(host["params"].to(dev), host["center3d"].to(dev), host["cube"].to(dev))
