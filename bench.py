@@ -489,7 +489,7 @@ def run_ours(args):
     other = {}
     if world == 1 and not args.no_other_configs:
         for name, b2 in (("C1_batch128", 128), ("batch1024", 1024)):
-            s2 = FitStep(layer, b2, CROP, use_graph=not args.no_graph, keep_pix_to_face=False)
+            s2 = mk(b2)                                 # same slice policy as the headline
             i2 = {k: torch.from_numpy(v).to(dev) for k, v in sample_fit_inputs(b2, seed=77).items()}
             s2.set_inputs(i2["params"], i2["center3d"], i2["cube"])
             s2.render_target(i2["params_target"])
