@@ -101,3 +101,45 @@ def test_row_run_packer_round_trip_cpu():
     assert np.array_equal(rebuilt[fg], d[fg])
     assert rows[B - 1, :, 1].sum() == 0 and rows[0, 10, 1] == 0
     assert p.nbytes < d.nbytes / 2
+
+
+def test_entry_points_validate_arguments_before_touching_the_device():
+    """Error behaviour of the C ABI (no GPU needed): bad arguments come back as DSF_ERR_BAD_ARG with a message, never
+    as a crash or a launch - null handles / buffers, a mis-aligned row-run table, an out-of-range crop size."""
+    import ctypes as C
+
+    from dsf_b200 import _lib
+
+    lib = _lib.load_library()
+    BAD = -1
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p).value
+    intr = (C.c_float * 4)(588.0, 587.0, 320.0, 240.0)
+    # fused step on the row-run target: null row table
+    rc = lib.dsf_fit_step_rows(None, 4, 128, p, p, p, p, p, p, None, None, None, 0, 0.1, 4, None, 0, None, intr,
+                               p, None, p, p, p, p, p, p, 0, None)
+    assert rc == BAD and b"row-run" in lib.dsf_last_error_string()
+    # mis-aligned row table (uint16 pairs are read as 32-bit words)
+    rc = lib.dsf_fit_step_rows(None, 4, 128, p, p, p, p, p, p, p + 2, p, p, 0, 0.1, 4, None, 0, None, intr,
+                               p, None, p, p, p, p, p, p, 0, None)
+    assert rc == BAD and b"aligned" in lib.dsf_last_error_string()
+    # invalid marker outside uint16
+    rc = lib.dsf_fit_step_rows(None, 4, 128, p, p, p, p, p, p, p, p, p, 70000, 0.1, 4, None, 0, None, intr,
+                               p, None, p, p, p, p, p, p, 0, None)
+    assert rc == BAD and b"uint16" in lib.dsf_last_error_string()
+    # plain fused step: null handle, crop size out of range
+    rc = lib.dsf_fit_step(None, 4, 128, p, p, p, p, p, p, p, 0.1, 4, None, 0, None, intr, p, None, p, p, p, p, p, p, 0, None)
+    assert rc == BAD
+    rc = lib.dsf_view_setup(0, 4, p, p, intr, 640, 480, 1024, None, p, p, p, None, None)
+    assert rc == BAD and b"[8,512]" in lib.dsf_last_error_string()
+    rc = lib.dsf_target_from_u16_rows(4, 1024, p, p, p, p, p, 0, p, None)
+    assert rc == BAD
+    # the host-side packer refuses instead of overrunning its payload buffer
+    import numpy as np
+    d = np.full((1, 8, 8), 700, np.uint16)
+    c = np.array([[0, 0, 800.0]], np.float32)
+    q = np.full((1, 3), 250.0, np.float32)
+    rows, off, pay = np.empty((1, 8, 2), np.uint16), np.empty(2, np.uint32), np.empty(10, np.uint16)
+    n = lib.dsf_pack_u16_rows(1, 8, d.ctypes.data, c.ctypes.data, q.ctypes.data, 0, rows.ctypes.data, off.ctypes.data,
+                              pay.ctypes.data, pay.size)
+    assert n == -1
