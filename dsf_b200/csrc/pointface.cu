@@ -254,7 +254,9 @@ face_sort_kernel(int V, int F, const float* __restrict__ verts, const int* __res
 }
 
 #define PF_GROUP 8       // faces per group sphere (PF_CHUNK is a multiple)
-#define PF_SUPER 4       // groups per super-group box
+#ifndef PF_SUPER
+#define PF_SUPER 2       // groups per super-group box (measured: 1 -> 2.06 ms, 2 -> 1.95, 3 -> 1.94, 4 -> 1.99, 8 -> 2.16)
+#endif
 #define PF_MAXCH 32      // chunk reordering is used up to this many chunks (7 for the MANO mesh)
 
 // squared distance from p to the box a = (lo.xyz, hi.x), b = (hi.y, hi.z)
@@ -470,7 +472,7 @@ point_face_fwd_kernel(int P, int V, int F, const float* __restrict__ points, con
 // ------------------------------------------------------------------------------------------------
 #define PFA_THREADS 1024
 #define PFA_WARPS (PFA_THREADS / 32)
-#define PFA_QA 136        // queue A: up to 32 lanes x PF_SUPER groups per lock step + 3 waiting
+#define PFA_QA (32 * PF_SUPER + 8)   // queue A: up to 32 lanes x PF_SUPER groups per lock step + 3 waiting
 #define PFA_QB 64         // queue B: up to 32 new pairs per stage-2 step + 31 waiting
 
 struct PfaSmem {
