@@ -928,18 +928,31 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
 #pragma unroll
                 for (int e = 0; e < 3; ++e) { pacc[9 + e] += gGt[e]; pacc[12 + e] -= gd[e]; }
             } else {
+                // several children (the five fingers at the wrist): shared-memory float atomics would be contended
+                // compare-and-swap loops.  The child parks its contribution in its own slot instead - entries 0..11
+                // (its consumed g_Gr, g_Gt) are free now - and the parent adds its children's slots in ascending
+                // joint order below (fixed summation order; the -gd term is recomputed there from the parked g_Gt).
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(&pacc[3 * r + c], up[3 * r + c] + gGt[r] * d[c]);
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    atomicAdd(&pacc[9 + e], gGt[e]);
-                    atomicAdd(&pacc[12 + e], -gd[e]);
-                }
+                    for (int c = 0; c < 3; ++c) acc[3 * r + c] = up[3 * r + c] + gGt[r] * d[c];
+                // acc[9..11] already hold g_Gt
             }
 #pragma unroll
             for (int e = 0; e < 3; ++e) acc[12 + e] += gd[e];        // own slot
+        }
+        __syncwarp();
+        if (topo.level[j] == lvl - 1 && topo.nchild[j] > 1) {
+            for (int c = 1; c < NJ; ++c)
+                if (topo.parents[c] == j) {
+                    const float* slot = s_acc[hl][c];
+                    float cg[3] = {slot[9], slot[10], slot[11]}, gdc[3];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) acc[e] += slot[e];
+                    mat3T_vec(Gr, cg, gdc);                          // this joint's Gr is the child's Pg
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) { acc[9 + e] += cg[e]; acc[12 + e] -= gdc[e]; }
+                }
         }
         __syncwarp();
     }
