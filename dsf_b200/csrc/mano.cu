@@ -414,13 +414,14 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     __syncthreads();
     // rows out: per hand 2 * BLEND_KPAD / 4 + NJ * RJ_STRIDE / 4 = 208 float4 (workspace rows are 16-byte aligned)
     constexpr int XQ = 2 * BLEND_KPAD / 4, RQ = NJ * RJ_STRIDE / 4;
-    for (int i = threadIdx.x; i < POSE_HPB * (XQ + RQ); i += POSE_HPB * NJ) {
-        const int h_ = i / (XQ + RQ), q = i % (XQ + RQ);
+    static_assert(RQ == POSE_HPB * NJ && XQ <= POSE_HPB * NJ, "one 16-byte piece of a hand's rows per thread");
+#pragma unroll
+    for (int h_ = 0; h_ < POSE_HPB; ++h_) {
         const int hd = blockIdx.x * POSE_HPB + h_;
-        if (hd >= B) continue;
+        if (hd >= B) break;
         float* row = ws + (size_t)hd * WS_PER_HAND;
-        if (q < XQ) reinterpret_cast<float4*>(row + WS_X)[q] = reinterpret_cast<const float4*>(s_X[h_])[q];
-        else reinterpret_cast<float4*>(row + WS_RJ)[q - XQ] = reinterpret_cast<const float4*>(s_out[h_])[q - XQ];
+        reinterpret_cast<float4*>(row + WS_RJ)[threadIdx.x] = reinterpret_cast<const float4*>(s_out[h_])[threadIdx.x];
+        if (threadIdx.x < XQ) reinterpret_cast<float4*>(row + WS_X)[threadIdx.x] = reinterpret_cast<const float4*>(s_X[h_])[threadIdx.x];
     }
 }
 
@@ -845,15 +846,18 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
     __shared__ __align__(16) float s_rj[POSE_HPB][NJ * RJ_STRIDE];
     __shared__ __align__(16) float s_ga[POSE_HPB][NJ * 12];
     __shared__ float s_gx[POSE_HPB][KP + 4];    // split-K partials of g_X summed per hand
-    for (int i = threadIdx.x; i < POSE_HPB * (NJ * RJ_STRIDE / 4 + NJ * 12 / 4); i += POSE_HPB * NJ) {
-        const int h_ = i / (NJ * RJ_STRIDE / 4 + NJ * 12 / 4), q = i % (NJ * RJ_STRIDE / 4 + NJ * 12 / 4);
+#pragma unroll
+    for (int h_ = 0; h_ < POSE_HPB; ++h_) {
         const int hs = min(blockIdx.x * POSE_HPB + h_, B - 1);
         const float* row = ws + (size_t)hs * WS_PER_HAND;
-        const bool is_rj = q < NJ * RJ_STRIDE / 4;
-        const float* src = is_rj ? row + WS_RJ + 4 * q : row + WS_GA + 4 * (q - NJ * RJ_STRIDE / 4);
-        float* dst = is_rj ? &s_rj[h_][4 * q] : &s_ga[h_][4 * (q - NJ * RJ_STRIDE / 4)];
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        // the records: NJ * RJ_STRIDE / 4 = 128 pieces = one per thread; g_A: 48 pieces
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_rj[h_][4 * threadIdx.x])),
+                     "l"(row + WS_RJ + 4 * threadIdx.x) : "memory");
+        if (threadIdx.x < NJ * 12 / 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_ga[h_][4 * threadIdx.x])),
+                         "l"(row + WS_GA + 4 * threadIdx.x) : "memory");
     }
+    static_assert(NJ * RJ_STRIDE / 4 == POSE_HPB * NJ, "one 16-byte piece of a hand's records per thread");
     stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);     // commits and waits for all copies
     const int hl = threadIdx.x / NJ;
     const int j = threadIdx.x % NJ;
