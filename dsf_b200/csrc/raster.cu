@@ -511,6 +511,7 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
                   float thr, float* __restrict__ parts_tile, int use_tma, CropParams crop, FusedTail tail,
                   TargetRows trows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint2 s_rowctx[ROWS ? RT_TH : 1];          // row-run target: (span record, payload offset) per tile row
     const RasterSmem s = carve_smem(smem_raw, R, F);
     // the loss target either as an fp32 plane or in the loader's row-run transport format (decoded in the epilogue)
     const bool has_target = target != nullptr || (ROWS && trows.rows != nullptr);
@@ -531,16 +532,17 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             const float* pa = target + ((size_t)mesh * R + ty0 + i / lines_per_row) * R + tx0 + (i % lines_per_row) * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
         }
-    } else if (ROWS && trows.rows && tid < 64) {
-        // row-run target: this hand's row records and packed pixels (a few KB) go to L2 now, behind the raster work
+    } else if (ROWS && trows.rows && tid < 96) {
+        // row-run target: this hand's row records and packed pixels (a few KB) go to L2 now, behind the raster work;
+        // one line per thread (64 lines = 8 KB of payload: a hand crop packs to ~6 KB; a longer payload is simply
+        // fetched on demand)
         if (tid < 32) {
             const char* rr = reinterpret_cast<const char*>(trows.rows + (size_t)mesh * R * 2);
-            for (int i = tid * 128; i < R * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rr + i));
+            if (tid * 128 < R * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rr + tid * 128));
         } else {
             const unsigned int p0 = __ldg(trows.hand_offset + mesh), p1 = __ldg(trows.hand_offset + mesh + 1);
-            const char* pp = reinterpret_cast<const char*>(trows.payload);
-            for (size_t i = ((size_t)p0 * 2 & ~(size_t)127) + (size_t)(tid - 32) * 128; i < (size_t)p1 * 2; i += 32 * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + i));
+            const char* pp = reinterpret_cast<const char*>(trows.payload) + ((size_t)p0 * 2 & ~(size_t)127);
+            if ((unsigned int)(tid - 32) * 64u < p1 - (p0 & ~63u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (tid - 32) * 128));
         }
     }
     if (use_tma) {
@@ -763,6 +765,32 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
             for (int i = lane; i < RT_WCANDS / 4; i += 32) z4[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
         }
+        if (ROWS && trows.rows && warp == 1 && (R & 3) == 0) {
+            // row-run target: (span record, payload offset) of every row of the tile, once per CTA.  One warp scan per
+            // 128 rows of the hand: lane l owns rows 4 l .. 4 l + 3 (one 128-bit load of their records); the exclusive
+            // prefix of the span lengths is each row's offset into the payload.
+            const unsigned int* r32 = reinterpret_cast<const unsigned int*>(trows.rows) + (size_t)mesh * R;
+            unsigned int carry = __ldg(trows.hand_offset + mesh);
+            for (int c0 = 0; c0 <= ty1; c0 += 128) {
+                const int q = c0 + 4 * lane;
+                uint4 rc = make_uint4(0u, 0u, 0u, 0u);
+                if (q + 3 < R) rc = __ldg(reinterpret_cast<const uint4*>(r32 + q));
+                const unsigned int rr[4] = {rc.x, rc.y, rc.z, rc.w};
+                const unsigned int e[4] = {0u, rc.x >> 16, (rc.x >> 16) + (rc.y >> 16), (rc.x >> 16) + (rc.y >> 16) + (rc.z >> 16)};
+                const unsigned int tot = e[3] + (rc.w >> 16);
+                unsigned int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const unsigned int excl = carry + incl - tot;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (q + i >= ty0 && q + i <= ty1) s_rowctx[q + i - ty0] = make_uint2(rr[i], excl + e[i]);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
         if (warp == 0) {
             if (has_t && crop.joints) crop_box_warp(crop, mesh, place_off, place_scale, lane, reinterpret_cast<CropBox*>(s.cands));
             if (grad_pre) {
@@ -834,40 +862,6 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         // (2) the list is processed with all lanes busy (a row through the hand has ~1/3 of its groups on the hand).
         const float bgval = __fdiv_rn(__fsub_rn(zmax, vw.zc), vw.zh);
         const int qw = tw >> 2;
-        // row-run target: lane r of the warp keeps the span record and the payload offset of the warp's r-th row
-        // (rows warp, warp + 16, ...: at most four of the 64-row tile); the offsets are prefix sums of the row lengths
-        unsigned int my_rec = 0u, my_off = 0u;
-        if (ROWS && trows.rows) {
-            // one warp scan per 128 rows: lane l owns rows 4 l .. 4 l + 3 (one 128-bit load of their records), the
-            // exclusive prefix of the lengths is each row's payload offset; the warp's rows fetch theirs by shuffle
-            const unsigned int* r32 = reinterpret_cast<const unsigned int*>(trows.rows) + (size_t)mesh * R;
-            unsigned int carry = __ldg(trows.hand_offset + mesh);
-            for (int c0 = 0; c0 < ty0 + th; c0 += 128) {
-                const int q = c0 + 4 * lane;
-                uint4 rc = make_uint4(0u, 0u, 0u, 0u);
-                if (q + 3 < R) rc = __ldg(reinterpret_cast<const uint4*>(r32 + q));       // R % 4 == 0 on this path
-                const unsigned int e1 = rc.x >> 16, e2 = e1 + (rc.y >> 16), e3 = e2 + (rc.z >> 16), tot = e3 + (rc.w >> 16);
-                unsigned int incl = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const unsigned int excl = carry + incl - tot;
-#pragma unroll
-                for (int r = 0; r < RT_TH / (RT_THREADS / 32); ++r) {
-                    const int ly = warp + r * (RT_THREADS / 32), g = ty0 + ly - c0;      // warp-uniform
-                    if (ly < th && g >= 0 && g < 128) {
-                        const int sub = g & 3;
-                        const unsigned int o_v = excl + (sub == 0 ? 0u : sub == 1 ? e1 : sub == 2 ? e2 : e3);
-                        const unsigned int r_v = sub == 0 ? rc.x : sub == 1 ? rc.y : sub == 2 ? rc.z : rc.w;
-                        const unsigned int o_g = __shfl_sync(0xffffffffu, o_v, g >> 2), r_g = __shfl_sync(0xffffffffu, r_v, g >> 2);
-                        if (lane == r) { my_off = o_g; my_rec = r_g; }
-                    }
-                }
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-        }
         // the four target values of a pixel group: fp32 plane, or decoded from the row's span (outside it the value
         // target_norm gives depth 0, which is bgval)
         auto target4 = [&](size_t o, unsigned int rec, unsigned int off, int x) -> float4 {
@@ -936,8 +930,8 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         const bool use_list = qw <= 32 && th <= 4 * (RT_THREADS / 32) && Fp * 2 >= (RT_THREADS / 32) * 128;
         int n_list = 0;
         for (int ly = warp, r = 0; ly < th; ly += RT_THREADS / 32, ++r) {
-            const unsigned int rec = ROWS ? __shfl_sync(0xffffffffu, my_rec, r & 31) : 0u;
-            const unsigned int off = ROWS ? __shfl_sync(0xffffffffu, my_off, r & 31) : 0u;
+            const uint2 rctx = ROWS ? s_rowctx[ly] : make_uint2(0u, 0u);        // (span record, payload offset) of this row
+            const unsigned int rec = rctx.x, off = rctx.y;
             for (int q4 = lane; q4 < ((qw + 31) & ~31); q4 += 32) {
                 const bool in = q4 < qw;
                 const int lx = q4 * 4;
@@ -983,13 +977,11 @@ raster_fwd_kernel(int R, int tiles_x, const float* __restrict__ verts, const flo
         }
         if (use_list) {
             __syncwarp();
-            for (int k0 = 0; k0 < n_list; k0 += 32) {
-                const int k = k0 + lane;
-                const int e = k < n_list ? glist[k] : 0;
-                const unsigned int rec = ROWS ? __shfl_sync(0xffffffffu, my_rec, e >> 5) : 0u;
-                const unsigned int off = ROWS ? __shfl_sync(0xffffffffu, my_off, e >> 5) : 0u;
-                if (k >= n_list) continue;
+            for (int k = lane; k < n_list; k += 32) {
+                const int e = glist[k];
                 const int ly = warp + (e >> 5) * (RT_THREADS / 32), lx = (e & 31) * 4;
+                const uint2 rctx = ROWS ? s_rowctx[ly] : make_uint2(0u, 0u);
+                const unsigned int rec = rctx.x, off = rctx.y;
                 float4 tg = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (has_target) tg = target4(((size_t)mesh * R + (ty0 + ly)) * R + (tx0 + lx), rec, off, tx0 + lx);
                 const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&s.key[ly * RT_TW + lx]);
