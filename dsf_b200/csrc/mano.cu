@@ -280,10 +280,15 @@ __device__ __forceinline__ void stage_pose_tables(float* s_comp, float* s_JS, co
     for (int i = tid; i < 45 * 45; i += nthr) s_comp[i] = __ldg(comp + i);
     for (int i = tid; i < 10 * NJ * 3; i += nthr) s_JS[i] = __ldg(JS + i);
 #else
-    for (int i = tid; i < 45 * 45; i += nthr)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_comp + i)), "l"(comp + i) : "memory");
-    for (int i = tid; i < 10 * NJ * 3; i += nthr)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_JS + i)), "l"(JS + i) : "memory");
+    // 16-byte pieces (both tables are cudaMalloc'ed, the shared arrays 16-byte aligned): 506 + 120 copies, then the
+    // last float of the 2025-entry basis on its own
+    for (int i = tid; i < (45 * 45) / 4; i += nthr)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_comp + 4 * i)), "l"(comp + 4 * i) : "memory");
+    for (int i = tid; i < (10 * NJ * 3) / 4; i += nthr)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_JS + 4 * i)), "l"(JS + 4 * i) : "memory");
+    if (tid == 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_comp + 45 * 45 - 1)), "l"(comp + 45 * 45 - 1) : "memory");
+    static_assert((10 * NJ * 3) % 4 == 0 && (45 * 45) % 4 == 1, "table sizes");
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
@@ -300,8 +305,8 @@ mano_pose_kernel(int B, DsfManoParams p, const float* __restrict__ comp, const f
     __shared__ float s_G[POSE_HPB][NJ][15];   // Gr[9] Gt[3] J[3]
     // the PCA basis and the rest-joint regressors are read 135 + 30 times per lane: stage them once per block
     // with coalesced loads instead of walking an 8 KB table through L1 one 180-byte row per iteration
-    __shared__ float s_comp[45 * 45];
-    __shared__ float s_JS[10 * NJ * 3];
+    __shared__ __align__(16) float s_comp[45 * 45 + 3];
+    __shared__ __align__(16) float s_JS[10 * NJ * 3];
     stage_pose_tables(s_comp, s_JS, comp, JS, threadIdx.x, POSE_HPB * NJ);
     __syncthreads();
     const int hl = threadIdx.x / NJ;
@@ -838,8 +843,8 @@ mano_pose_bwd_kernel(int B, DsfManoParams p, DsfManoGrads g, const float* __rest
                      LossFold lf) {
     __shared__ float s_acc[POSE_HPB][NJ][15];   // gGr[9] gGt[3] gJ[3]
     __shared__ float s_gang[POSE_HPB][48];
-    __shared__ float s_comp[45 * 45];           // staged once per block, see mano_pose_kernel
-    __shared__ float s_JS[10 * NJ * 3];
+    __shared__ __align__(16) float s_comp[45 * 45 + 3];   // staged once per block, see mano_pose_kernel
+    __shared__ __align__(16) float s_JS[10 * NJ * 3];
     // every per-hand input of the block (the joints' forward records and the skinning cotangent g_A: 2.75 KB per
     // hand) is staged with 16-byte cp.async copies issued together with the tables: nothing in the kernel then waits
     // on a dependent global load (the tree walk used to fetch the parent's record from the workspace at every level)
