@@ -1,8 +1,11 @@
 // dsf_b200 - point-to-mesh-face squared distance for sm_100a (forward arg-min + backward).
 // Replaces pytorch3d-0.4.0 _C.point_face_dist_forward/_backward as wrapped by metric/meshLoss.py:21-70
 // (ICPLoss :347-353, JointICPLoss :377-394).  DSF always passes one face list for the whole batch, so
-// no packing / first_idx tables are needed: grid = (point chunks, hands), the hand's triangles are
-// staged in shared memory once per CTA and every thread scans them for its own point.
+// no packing / first_idx tables are needed.  Two forward kernels with identical results (the exhaustive scan's
+// minimum and lowest-index arg-min): point_face_fwd_all_kernel - one CTA per hand stages every face record and a
+// box hierarchy once, warps pull 32-point batches and evaluate the surviving pairs with full warps (sorted points
+// and faces, meshes up to 2047 faces: the MANO case) - and point_face_fwd_kernel, thread per point over chunks of
+// staged records (any mesh size, unsorted input).
 #include <math.h>
 
 #include "common.cuh"

@@ -389,6 +389,9 @@ extern "C" int dsf_crop_hand(int batch, int R, const float* img, const float* jo
 //                                 candidate list in shared memory
 //   phase C  lane per candidate : full oracle-order fragment evaluation + early z + atomicMin on the key
 // A batch whose runs exceed the list is evaluated in place, so any mesh / crop size is handled.
+// Epilogue (fused step): background fill + normalisation + m2d loss sums + the raster backward (integer face
+// moments, closed-form face gradients, fixed-point vertex scatter), see the comments there.  Template ROWS: the
+// loss target arrives as the loader's row-run packed sensor crop and is decoded where it is compared.
 // ------------------------------------------------------------------------------------------------
 #define RT_TW 128            // tile width  (pixels)
 #define RT_TH 64             // tile height: 64 KB of keys -> two CTAs per SM
